@@ -1,0 +1,216 @@
+/*
+ * ovb200.h — C ABI of the B200 (sm_100a) hot-path library `libovb200.so`.
+ *
+ * The reference (SAIS-FUXI/Omni-Video) is pure Python/PyTorch and has no FFI of its own: every
+ * FLOP on its denoising hot path goes through a library call made by PyTorch.
+ * Each entry point below replaces one such call site (or a fused group of them); the comment above
+ * each function names the reference file:line it stands in for.  The Python binding a maintainer
+ * adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; pointers are DEVICE pointers unless stated otherwise;
+ *   - no allocation, no synchronisation, no global state: the caller owns every buffer and passes
+ *     the CUDA stream (a `cudaStream_t` passed as `void*`);
+ *   - returns OVB_OK (0) or a negative error code; `ovb_last_error()` returns a thread-local,
+ *     human-readable description of the last failure; nothing throws across the ABI;
+ *   - bf16 tensors are `uint16_t`-sized IEEE bfloat16, row-major; "ld*" are leading dimensions in
+ *     ELEMENTS; every bf16 row pitch must be a multiple of 8 elements (16 bytes) and every base
+ *     pointer 16-byte aligned.
+ */
+#ifndef OVB200_H_
+#define OVB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVB_OK 0
+#define OVB_ERR_INVALID_ARGUMENT (-1)
+#define OVB_ERR_CUDA (-2)
+#define OVB_ERR_UNSUPPORTED_ARCH (-3)
+
+#define OVB_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+int ovb_abi_version(void);
+const char* ovb_last_error(void);
+/* Fails with OVB_ERR_UNSUPPORTED_ARCH unless the current device is compute capability 10.x. */
+int ovb_check_device(void);
+/* Number of kernels this library has launched from the calling process (bench `gpu_launches`). */
+int64_t ovb_launch_count(void);
+
+/* ---- GEMM (tcgen05 / TMEM / TMA) ------------------------------------------------------------
+ * out = epilogue( A[M,K] * W[N,K]^T + bias[N] )       bf16 operands, fp32 accumulation in TMEM.
+ * Replaces every nn.Linear on the DiT path (reference omnivideo/modules/model.py:118-121 q/k/v/o,
+ * :211-213 ffn, :384-388 patch/text embedding) together with the elementwise work the reference
+ * runs right after it (model.py:245-246, :250, :253-254).
+ *
+ * epilogue:
+ *   OVB_EPI_BF16            out(bf16)  = acc + bias
+ *   OVB_EPI_GELU_BF16       out(bf16)  = gelu_tanh(bf16(acc + bias))               (model.py:212)
+ *   OVB_EPI_RESID_F32       out(fp32)  = resid + bf16(acc + bias)                  (model.py:250)
+ *   OVB_EPI_GATE_RESID_F32  out(fp32)  = resid + bf16(acc + bias) * gate           (model.py:246,254)
+ *   OVB_EPI_F32             out(fp32)  = acc + bias
+ *
+ * gate is fp32; element (row r, col n) is read at
+ *   gate[(r / rows_per_sample) * gate_sample_stride + (r % rows_per_sample) * gate_row_stride + n]
+ * so a per-sample vector uses gate_row_stride = 0 and a per-token table uses gate_row_stride = ld.
+ *
+ * Sequence-parallel layouts, both optional:
+ *   n_split  > 1 : the N output columns are cut into n_split equal groups; group g is written as its
+ *                  own row-major [M, N/n_split] matrix at out + g * out_split_stride (elements),
+ *                  i.e. straight into the Ulysses all-to-all send layout (N/n_split % 32 == 0).
+ *   k_split  > 1 : A is given as k_split row-major [M, K/k_split] matrices, the g-th at
+ *                  A + g * a_split_stride (elements): the all-to-all receive layout
+ *                  (K/k_split % 64 == 0).
+ */
+#define OVB_EPI_BF16 0
+#define OVB_EPI_GELU_BF16 1
+#define OVB_EPI_RESID_F32 2
+#define OVB_EPI_GATE_RESID_F32 3
+#define OVB_EPI_F32 4
+
+typedef struct ovb_gemm_args {
+  const void* A;      /* bf16 [M, K] (or k_split x [M, K/k_split]) */
+  int64_t lda;
+  const void* W;      /* bf16 [N, K]  (nn.Linear weight layout [out, in]) */
+  int64_t ldw;
+  const void* bias;   /* bf16 [N] or NULL */
+  void* out;          /* bf16 or fp32 [M, N] per epilogue */
+  int64_t ldo;
+  int32_t M, N, K;
+  int32_t epilogue;
+  const void* resid;  /* fp32 [M, N], ld = ldr (RESID / GATE_RESID); may alias out */
+  int64_t ldr;
+  const void* gate;   /* fp32, see above (GATE_RESID) */
+  int64_t gate_row_stride;
+  int64_t gate_sample_stride;
+  int32_t rows_per_sample;
+  int32_t n_split;          /* <=1: off */
+  int64_t out_split_stride;
+  int32_t k_split;          /* <=1: off */
+  int64_t a_split_stride;
+} ovb_gemm_args;
+
+int ovb_gemm_bf16(const ovb_gemm_args* args, void* stream);
+
+/* ---- flash attention forward (tcgen05 / TMEM / TMA) ----------------------------------------
+ * out[b, i, h, :] = softmax_j( scale * <q[b,i,h,:], k[b,j,h,:]> , j < k_lens[b] ) * v[b, j, h, :]
+ * head_dim = 128, non-causal, bf16 in / bf16 out, fp32 softmax statistics.
+ * Replaces flash_attention() (reference omnivideo/modules/attention.py:24-133 -> flash_attn
+ * varlen kernels at :96/:116) for the two call sites model.py:144-149 (self) and :174 (cross).
+ * q/k/v/out are [B, L, H, 128] views: element (b, l, h, c) at
+ *   ptr + b * batch_stride + l * row_stride + h * 128 + c      (strides in elements)
+ * which lets q, k and v live inside one fused [L, 3*H*128] projection buffer.
+ * k_lens: HOST pointer to B int32 (valid keys per sample) or NULL (= Lk for all).
+ */
+typedef struct ovb_attn_args {
+  const void* q; int64_t q_row_stride; int64_t q_batch_stride;
+  const void* k; int64_t k_row_stride; int64_t k_batch_stride;
+  const void* v; int64_t v_row_stride; int64_t v_batch_stride;
+  void* out;     int64_t o_row_stride; int64_t o_batch_stride;
+  int32_t B, H, Lq, Lk;
+  const int32_t* k_lens;  /* host, may be NULL */
+  float softmax_scale;    /* <=0: 1/sqrt(128) */
+} ovb_attn_args;
+
+int ovb_attn_fwd(const ovb_attn_args* args, void* stream);
+
+/* ---- LayerNorm (+ AdaLN modulation or affine) ------------------------------------------------
+ * y = LN_eps(x) * a + b over the last dim (fp32 statistics, two-pass like torch.layer_norm).
+ * Replaces WanLayerNorm + modulation (reference model.py:87-97, :243, :252, :286-289) and the
+ * affine norm3 (:205-207, :250).
+ *   mode OVB_LN_MODULATE : a = 1 + scale, b = shift   (fp32 vectors/tables)
+ *   mode OVB_LN_AFFINE   : a = weight,    b = bias    (bf16 [d])
+ * scale/shift element (row r, col c):
+ *   p[(r / rows_per_sample) * mod_sample_stride + (r % rows_per_sample) * mod_row_stride + c]
+ * x is fp32 (x_is_bf16 = 0) or bf16; with round_ln_bf16 != 0 the normalised value is rounded to
+ * bf16 before modulation (what `.type_as(x)` does for a bf16 residual stream, model.py:97).
+ * out is bf16 (out_is_f32 = 0) or fp32.
+ */
+#define OVB_LN_MODULATE 0
+#define OVB_LN_AFFINE 1
+
+typedef struct ovb_ln_args {
+  const void* x; int64_t ldx; int32_t x_is_bf16;
+  void* out;     int64_t ldo; int32_t out_is_f32;
+  int32_t rows, d;
+  float eps;
+  int32_t mode;
+  const void* a;  /* MODULATE: fp32 scale ; AFFINE: bf16 weight */
+  const void* b;  /* MODULATE: fp32 shift ; AFFINE: bf16 bias   */
+  int64_t mod_row_stride, mod_sample_stride;
+  int32_t rows_per_sample;
+  int32_t round_ln_bf16;
+} ovb_ln_args;
+
+int ovb_layernorm(const ovb_ln_args* args, void* stream);
+
+/* ---- RMSNorm over the full model dim (+ optional 3-D RoPE), in place ----------------------------
+ * For every row: t = bf16( x * rsqrt(mean_d(x^2) + eps) ) * weight ; then, if rope != 0, each head's
+ * 64 interleaved pairs (x[2j], x[2j+1]) are rotated by the angle of the token's (frame,row,col).
+ * Replaces WanRMSNorm (reference model.py:68-84, :137-138, :169-170) and rope_apply (:37-65;
+ * sequence-parallel variant distributed/full_sequence_parallel.py:22-60).
+ * x: bf16 [rows, d] with leading dim ldx, optionally cut into col_split column groups of
+ *    d/col_split columns, group g at x + g * col_split_stride (the all-to-all send layout).
+ * cs_table: fp32 [table_len, 64, 2] = (cos, sin) of reference `freqs` (model.py:405-411).
+ * Token index of row r (within sample) is token_offset + r % rows_per_sample; tokens >= F*H*W are
+ * left unrotated (model.py:61; full_sequence_parallel.py:9-19).
+ */
+typedef struct ovb_rmsnorm_rope_args {
+  void* x; int64_t ldx;
+  int32_t rows, d;
+  const void* weight;  /* bf16 [d] */
+  float eps;
+  int32_t rope;        /* 0: RMSNorm only */
+  const float* cs_table; int32_t table_len;
+  int32_t F, H, W;
+  int32_t rows_per_sample;
+  int32_t token_offset;
+  int32_t col_split; int64_t col_split_stride;
+} ovb_rmsnorm_rope_args;
+
+int ovb_rmsnorm_rope(const ovb_rmsnorm_rope_args* args, void* stream);
+
+/* ---- patchify / unpatchify ---------------------------------------------------------------------
+ * patchify: latent x [C, F, H, W] (fp32 or bf16) -> tokens bf16 [F*(H/2)*(W/2), C*4]; column index
+ * (c*2 + ph)*2 + pw matches patch_embedding.weight.flatten(1) (reference model.py:384, :455-458).
+ * unpatchify: head output fp32 [L, 4*C] (column (ph*2+pw)*C + c) -> fp32 [C, F, 2*Hp, 2*Wp]
+ * (reference model.py:526-549, einsum 'fhwpqrc->cfphqwr').
+ */
+int ovb_patchify(const void* x, int32_t x_is_bf16, void* tokens, int64_t ldt, int32_t C, int32_t F,
+                 int32_t H, int32_t W, void* stream);
+int ovb_unpatchify(const float* y, int64_t ldy, float* out, int32_t C, int32_t F, int32_t Hp,
+                   int32_t Wp, void* stream);
+
+/* ---- small fp32 linears ------------------------------------------------------------------------
+ * out[M, N] (fp32) = act_out( act_in(x[M, K]) * W[N, K]^T + bias ), fp32 math on bf16-stored weights:
+ * what the reference's `autocast('cuda', dtype=float32)` regions compute (time_embedding /
+ * time_projection model.py:390-392, :469-476; head.head :285-289).
+ * act: 0 none, 1 SiLU.   x fp32 [M, K] (ldx), W bf16 [N, K] (ldw), bias bf16 [N] or NULL.
+ */
+int ovb_linear_f32(const float* x, int64_t ldx, const void* W, int64_t ldw, const void* bias,
+                   float* out, int64_t ldo, int32_t M, int32_t N, int32_t K, int32_t act_in,
+                   int32_t act_out, void* stream);
+
+/* Sinusoidal timestep embedding, fp64 math -> fp32 [n, dim]: cos(t*f_i) || sin(t*f_i),
+ * f_i = 10000^(-i/(dim/2))   (reference model.py:13-23).  t: fp32 device [n]. */
+int ovb_sinusoidal_embedding(const float* t, float* out, int32_t n, int32_t dim, void* stream);
+
+/* AdaLN modulation tables, built once per forward:
+ *   out[l, b, k, c] (fp32) = float(mod[l, k, c]) + e[b, e_has_k ? k*d + c : c]
+ * mod: bf16 [n_layers, K, d] (stacked `blocks.{l}.modulation`, K = 6, reference model.py:216,238;
+ * or `head.modulation`, K = 2, n_layers = 1, e_has_k = 0, :276,286); e: fp32 [B, K*d] or [B, d]. */
+int ovb_modulation_table(const void* mod, const float* e, float* out, int32_t n_layers, int32_t B,
+                         int32_t K, int32_t d, int32_t e_has_k, void* stream);
+
+/* fp32 -> bf16 / bf16 -> fp32 casts of n contiguous elements (n % 8 == 0). */
+int ovb_cast_f32_to_bf16(const float* x, void* out, int64_t n, void* stream);
+int ovb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVB200_H_ */

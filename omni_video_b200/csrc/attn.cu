@@ -1,0 +1,389 @@
+// ovb_attn_fwd: flash-attention forward for sm_100a (head_dim 128, non-causal, key-length mask).
+//
+// One CTA = 256 query rows of one (batch, head): two 128-row Q tiles that ping-pong on the tensor
+// core so that the softmax of one tile overlaps the MMAs of the other.
+//   warp 0        TMA producer: Q (once), then K_j / V_j 128-row tiles into two 2-stage rings
+//   warp 1        one thread issues tcgen05.mma:  S_i = Q_i K_j^T  (SS, both K-major)  and
+//                 O_i += P_i V_j  (TS: P read from TMEM, V MN-major from shared memory)
+//   warp 2        TMEM allocator (512 columns: S0 | S1 | O0 | O1, each 128 lanes x 128 fp32)
+//   warps 4-7     softmax warpgroup for Q tile 0 : one thread per query row
+//   warps 8-11    softmax warpgroup for Q tile 1
+// Per KV tile a softmax thread reads its S row (tcgen05.ld), keeps a running max with LAZY
+// rescaling (O and the row sum are only rescaled when the max grows by more than 2^8, which also
+// makes a separate correction warpgroup unnecessary: "S_j ready" implies "P_{j-1} V_{j-1} done",
+// so the owner of the row can rescale O in TMEM itself), exponentiates with ex2.approx in the
+// log2 domain, and writes bf16 P over the first 64 columns of its own S region (tcgen05.st).
+// Keys >= k_len are masked to -inf; K/V rows past the tensor end are zero-filled by TMA.
+//
+// FLOPs per CTA-step (one KV tile, both Q tiles): 4 * 128*128*128 MACs; bytes from L2: 64 KB.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace ovb {
+
+constexpr int kAttnThreads = 384;
+constexpr int kTileBytes = 128 * 128 * 2;  // 32 KB : one 128x128 bf16 tile (two 64-col TMA boxes)
+constexpr int kBoxBytes = 128 * 64 * 2;    // 16 KB
+constexpr int kKVStages = 2;
+constexpr int kAttnSmem = 2 * kTileBytes + 2 * kKVStages * kTileBytes + 1024 + 256;
+
+// TMEM column map
+constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
+
+struct AttnParams {
+  __nv_bfloat16* out;
+  long long o_row_stride, o_batch_stride;
+  int Lq, Lk, H;
+  float scale_log2;  // softmax_scale * log2(e)
+  int kl0, kl1, kl2, kl3, kl4, kl5, kl6, kl7;  // per-sample valid keys (B <= 8)
+};
+
+__device__ __forceinline__ void setmaxnreg_dec_72() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+}
+__device__ __forceinline__ void setmaxnreg_inc_216() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                                  // 2 tiles
+  uint8_t* sK = sQ + 2 * kTileBytes;                   // kKVStages tiles
+  uint8_t* sV = sK + kKVStages * kTileBytes;           // kKVStages tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * kTileBytes);
+  uint64_t* q_full = bars;          // [1]
+  uint64_t* k_full = bars + 1;      // [2]
+  uint64_t* k_empty = bars + 3;     // [2]
+  uint64_t* v_full = bars + 5;      // [2]
+  uint64_t* v_empty = bars + 7;     // [2]
+  uint64_t* s_full = bars + 9;      // [2] per Q tile
+  uint64_t* p_full = bars + 11;     // [2] per Q tile
+  uint64_t* o_full = bars + 13;     // [2] per Q tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_blk = blockIdx.x;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int k_len = batch == 0 ? p.kl0 : batch == 1 ? p.kl1 : batch == 2 ? p.kl2 : batch == 3 ? p.kl3
+                  : batch == 4 ? p.kl4 : batch == 5 ? p.kl5 : batch == 6 ? p.kl6 : p.kl7;
+  const int n_kv = (k_len + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec_72();
+    if (warp == 0 && lane == 0 && n_kv > 0) {
+      // -------------------------------------------------------- TMA producer
+      const int col = head * 128;
+      mbar_expect_tx(q_full, 2 * kTileBytes);
+      for (int i = 0; i < 2; ++i) {
+        const int row = q_blk * 256 + i * 128;
+        tma_load_3d(sQ + i * kTileBytes, &tmQ, q_full, col, row, batch);
+        tma_load_3d(sQ + i * kTileBytes + kBoxBytes, &tmQ, q_full, col + 64, row, batch);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], kTileBytes);
+        tma_load_3d(sK + s * kTileBytes, &tmK, &k_full[s], col, j * 128, batch);
+        tma_load_3d(sK + s * kTileBytes + kBoxBytes, &tmK, &k_full[s], col + 64, j * 128, batch);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], kTileBytes);
+        tma_load_3d(sV + s * kTileBytes, &tmV, &v_full[s], col, j * 128, batch);
+        tma_load_3d(sV + s * kTileBytes + kBoxBytes, &tmV, &v_full[s], col + 64, j * 128, batch);
+      }
+    } else if (warp == 1 && lane == 0 && n_kv > 0) {
+      // -------------------------------------------------------- MMA issuer
+      const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // V is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t k_addr = smem_u32(sK);
+      const uint32_t v_addr = smem_u32(sV);
+
+      auto issue_qk = [&](int i, int s) {
+        const uint32_t qa = q_addr + i * kTileBytes;
+        const uint32_t ka = k_addr + s * kTileBytes;
+        const uint32_t d = tmem_base + (i == 0 ? kColS0 : kColS1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+          umma_ss(d, umma_desc_sw128(qa + off, 16, 1024), umma_desc_sw128(ka + off, 16, 1024),
+                  idesc_qk, kk != 0);
+        }
+      };
+      auto issue_pv = [&](int i, int s, bool first) {
+        const uint32_t va = v_addr + s * kTileBytes;
+        const uint32_t pt = tmem_base + (i == 0 ? kColS0 : kColS1);
+        const uint32_t d = tmem_base + (i == 0 ? kColO0 : kColO1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          // 16 kv rows per MMA: 2048 B down the V tile; second 64 columns are kBoxBytes away (LBO)
+          umma_ts(d, pt + kk * 8, umma_desc_sw128(va + kk * 2048, kBoxBytes, 1024), idesc_pv,
+                  !(first && kk == 0));
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        mbar_wait(&k_full[s], ph);
+        tc_fence_after();
+        issue_qk(0, s);
+        umma_commit(&s_full[0]);
+        if (j > 0) {
+          const int sp = (j - 1) % kKVStages;
+          mbar_wait(&p_full[1], (j - 1) & 1);
+          tc_fence_after();
+          issue_pv(1, sp, j - 1 == 0);
+          umma_commit(&v_empty[sp]);
+        }
+        issue_qk(1, s);
+        umma_commit(&s_full[1]);
+        umma_commit(&k_empty[s]);
+        mbar_wait(&p_full[0], j & 1);
+        mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+        issue_pv(0, s, j == 0);
+      }
+      umma_commit(&o_full[0]);
+      {
+        const int sp = (n_kv - 1) % kKVStages;
+        mbar_wait(&p_full[1], (n_kv - 1) & 1);
+        tc_fence_after();
+        issue_pv(1, sp, n_kv - 1 == 0);
+        umma_commit(&v_empty[sp]);
+        umma_commit(&o_full[1]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------- softmax warpgroups
+    setmaxnreg_inc_216();
+    const int wg = (warp - 4) >> 2;  // Q tile index
+    const int quad = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + (wg == 0 ? kColS0 : kColS1);
+    const uint32_t tO = tmem_base + lane_base + (wg == 0 ? kColO0 : kColO1);
+    const int q_row = q_blk * 256 + wg * 128 + quad * 32 + lane;
+    const float scale = p.scale_log2;
+
+    float m_used = -INFINITY;  // reference max (raw score units) the exponentials are taken against
+    float l_sum = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[wg], j & 1);
+      tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + c * 32, r);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) s[c * 32 + t] = __uint_as_float(r[t]);
+      }
+      tmem_wait_ld();
+      const int valid = k_len - j * 128;  // >= 1
+      if (valid < 128) {
+#pragma unroll
+        for (int t = 0; t < 128; ++t) s[t] = t < valid ? s[t] : -INFINITY;
+      }
+      float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
+#pragma unroll
+      for (int t = 4; t < 128; t += 4) {
+        m0 = fmaxf(m0, s[t]);
+        m1 = fmaxf(m1, s[t + 1]);
+        m2 = fmaxf(m2, s[t + 2]);
+        m3 = fmaxf(m3, s[t + 3]);
+      }
+      const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      // lazy rescale: only when some row of this warp grew its max by more than 2^8
+      const bool grow = (m_tile - m_used) * scale > 8.0f;  // true on the first tile (m_used=-inf)
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_used, m_tile);
+        const float alpha = fast_exp2((m_used - m_new) * scale);  // 0 on the first tile
+        l_sum *= alpha;
+        m_used = m_new;
+        if (j > 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tO + c * 32, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) r[t] = __float_as_uint(__uint_as_float(r[t]) * alpha);
+            tmem_st32(tO + c * 32, r);
+          }
+        }
+      }
+      const float neg_m = -m_used * scale;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 4) {
+          const float e0 = fast_exp2(fmaf(s[c * 32 + t], scale, neg_m));
+          const float e1 = fast_exp2(fmaf(s[c * 32 + t + 1], scale, neg_m));
+          const float e2 = fast_exp2(fmaf(s[c * 32 + t + 2], scale, neg_m));
+          const float e3 = fast_exp2(fmaf(s[c * 32 + t + 3], scale, neg_m));
+          a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+          pk[t / 2] = pack_bf16x2(e0, e1);
+          pk[t / 2 + 1] = pack_bf16x2(e2, e3);
+        }
+        tmem_st16(tS + c * 16, pk);
+      }
+      l_sum += (a0 + a1) + (a2 + a3);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[wg]);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global (one 256-byte row segment per thread)
+    const bool row_ok = q_row < p.Lq;
+    __nv_bfloat16* orow = p.out + static_cast<long long>(batch) * p.o_batch_stride +
+                          static_cast<long long>(q_row) * p.o_row_stride + head * 128;
+    if (n_kv > 0) {
+      mbar_wait(&o_full[wg], 0);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_sum;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tO + c * 32, r);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+            o.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+            o.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+            o.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+          }
+        }
+      }
+    } else if (row_ok) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int g = 0; g < 16; ++g) *reinterpret_cast<uint4*>(orow + g * 8) = z;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace ovb
+
+extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(a != nullptr, "ovb_attn_fwd: null args");
+  OVB_CHECK_ARG(a->q && a->k && a->v && a->out, "ovb_attn_fwd: null q/k/v/out");
+  OVB_CHECK_ARG(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0,
+                "ovb_attn_fwd: bad shape B=%d H=%d Lq=%d Lk=%d", a->B, a->H, a->Lq, a->Lk);
+  OVB_CHECK_ARG(a->B <= 8, "ovb_attn_fwd: B <= 8 supported (got %d)", a->B);
+  OVB_CHECK_ARG(a->q_row_stride % 8 == 0 && a->k_row_stride % 8 == 0 && a->v_row_stride % 8 == 0 &&
+                    a->o_row_stride % 8 == 0 && a->q_batch_stride % 8 == 0 &&
+                    a->k_batch_stride % 8 == 0 && a->v_batch_stride % 8 == 0 &&
+                    a->o_batch_stride % 8 == 0,
+                "ovb_attn_fwd: strides must be multiples of 8 elements");
+  OVB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
+                 reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->out)) % 16 == 0,
+                "ovb_attn_fwd: pointers must be 16-byte aligned");
+
+  CUtensorMap tmQ, tmK, tmV;
+  const uint32_t box[3] = {64, 128, 1};
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(a->H) * 128, static_cast<uint64_t>(a->Lq),
+                              static_cast<uint64_t>(a->B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(a->q_row_stride) * 2,
+                                 static_cast<uint64_t>(a->B > 1 ? a->q_batch_stride
+                                                                : a->q_row_stride * a->Lq) * 2};
+    int rc = encode_tmap_bf16(&tmQ, a->q, 3, dims, strides, box);
+    if (rc != OVB_OK) return rc;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(a->H) * 128, static_cast<uint64_t>(a->Lk),
+                              static_cast<uint64_t>(a->B)};
+    const uint64_t ks[2] = {static_cast<uint64_t>(a->k_row_stride) * 2,
+                            static_cast<uint64_t>(a->B > 1 ? a->k_batch_stride
+                                                           : a->k_row_stride * a->Lk) * 2};
+    int rc = encode_tmap_bf16(&tmK, a->k, 3, dims, ks, box);
+    if (rc != OVB_OK) return rc;
+    const uint64_t vs[2] = {static_cast<uint64_t>(a->v_row_stride) * 2,
+                            static_cast<uint64_t>(a->B > 1 ? a->v_batch_stride
+                                                           : a->v_row_stride * a->Lk) * 2};
+    rc = encode_tmap_bf16(&tmV, a->v, 3, dims, vs, box);
+    if (rc != OVB_OK) return rc;
+  }
+
+  AttnParams p;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.o_row_stride = a->o_row_stride;
+  p.o_batch_stride = a->o_batch_stride;
+  p.Lq = a->Lq;
+  p.Lk = a->Lk;
+  p.H = a->H;
+  const float scale = a->softmax_scale > 0.f ? a->softmax_scale : 0.08838834764831845f;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  int kls[8];
+  for (int b = 0; b < 8; ++b) {
+    int kl = a->Lk;
+    if (a->k_lens != nullptr && b < a->B) kl = a->k_lens[b];
+    OVB_CHECK_ARG(kl >= 0 && kl <= a->Lk, "ovb_attn_fwd: k_lens[%d]=%d outside [0, %d]", b, kl,
+                  a->Lk);
+    kls[b] = kl;
+  }
+  p.kl0 = kls[0]; p.kl1 = kls[1]; p.kl2 = kls[2]; p.kl3 = kls[3];
+  p.kl4 = kls[4]; p.kl5 = kls[5]; p.kl6 = kls[6]; p.kl7 = kls[7];
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    attr_set = true;
+  }
+  dim3 grid((a->Lq + 255) / 256, a->H, a->B);
+  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK,
+                                                                                        tmV, p);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}

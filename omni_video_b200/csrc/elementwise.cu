@@ -1,0 +1,506 @@
+// HBM-bound kernels of the DiT hot path: LayerNorm + AdaLN modulation, full-width RMSNorm + 3-D RoPE,
+// patchify / unpatchify, sinusoidal timestep embedding, casts.  All use 16-byte vector accesses,
+// one CTA per row (d/8 threads, one 8-element vector per thread) so a row is read exactly once;
+// algorithmic bytes per element are listed at each kernel (DESIGN.md §4 / SURVEY.md §8(d)).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace ovb {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  // red: >= 32 floats of shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  __syncthreads();  // protect red from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = lane < nwarps ? red[lane] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 w = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm + modulation.  Bytes/element: 4 (fp32 x) + 2 (bf16 y) = 6 (+ L2-resident vectors).
+struct LnParams {
+  const void* x; long long ldx; int x_is_bf16;
+  void* out; long long ldo; int out_is_f32;
+  int rows, d;
+  float eps;
+  int mode;
+  const void* a; const void* b;
+  long long mod_row_stride, mod_sample_stride;
+  int rows_per_sample;
+  int round_ln_bf16;
+};
+
+__global__ void layernorm_kernel(const LnParams p) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int c0 = threadIdx.x * 8;
+  const bool active = c0 < p.d;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (active) {
+    if (p.x_is_bf16)
+      load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx + c0, v);
+    else
+      load8_f32(reinterpret_cast<const float*>(p.x) + row * p.ldx + c0, v);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+  const float mean = block_sum(s, red) / p.d;
+  float q = 0.f;
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = v[j] - mean;
+      q += t * t;
+    }
+  }
+  const float var = block_sum(q, red) / p.d;
+  const float rstd = rsqrtf(var + p.eps);
+  if (!active) return;
+
+  float y[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    y[j] = (v[j] - mean) * rstd;
+    if (p.round_ln_bf16) y[j] = bf16_round(y[j]);
+  }
+  if (p.mode == OVB_LN_MODULATE) {
+    const int sample = row / p.rows_per_sample;
+    const int r_in = row - sample * p.rows_per_sample;
+    const long long off = sample * p.mod_sample_stride + r_in * p.mod_row_stride + c0;
+    float sc[8], sh[8];
+    load8_f32(reinterpret_cast<const float*>(p.a) + off, sc);
+    load8_f32(reinterpret_cast<const float*>(p.b) + off, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = y[j] * (1.0f + sc[j]) + sh[j];
+  } else {
+    float w[8], bb[8];
+    load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.a) + c0, w);
+    load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.b) + c0, bb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = y[j] * w[j] + bb[j];
+  }
+  if (p.out_is_f32)
+    store8_f32(reinterpret_cast<float*>(p.out) + row * p.ldo + c0, y);
+  else
+    store8_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + c0, y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm over full d + RoPE, in place on bf16.  Bytes/element: 2 + 2 = 4.
+struct RmsRopeParams {
+  __nv_bfloat16* x; long long ldx;
+  int rows, d;
+  const __nv_bfloat16* weight;
+  float eps;
+  int rope;
+  const float2* cs;  // [table_len][64] (cos, sin)
+  int table_len;
+  int F, H, W;
+  int rows_per_sample, token_offset;
+  int cols_per_split; long long col_split_stride;
+};
+
+__global__ void rmsnorm_rope_kernel(const RmsRopeParams p) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int c0 = threadIdx.x * 8;
+  const bool active = c0 < p.d;
+  __nv_bfloat16* ptr = nullptr;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (active) {
+    const int seg = c0 / p.cols_per_split;
+    ptr = p.x + seg * p.col_split_stride + row * p.ldx + (c0 - seg * p.cols_per_split);
+    load8_bf16(ptr, v);
+  }
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q += v[j] * v[j];
+  const float ms = block_sum(q, red) / p.d;
+  const float rinv = rsqrtf(ms + p.eps);
+  if (!active) return;
+  float w[8];
+  load8_bf16(p.weight + c0, w);
+  float y[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = bf16_round(bf16_round(v[j] * rinv) * w[j]);
+
+  if (p.rope) {
+    const int tok = p.token_offset + row % p.rows_per_sample;
+    if (tok < p.F * p.H * p.W) {
+      const int hw = p.H * p.W;
+      const int f = tok / hw;
+      const int rem = tok - f * hw;
+      const int h = rem / p.W;
+      const int w_ = rem - h * p.W;
+      const int pair0 = (c0 & 127) >> 1;  // first of 4 consecutive pairs inside the head
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pr = pair0 + j;
+        const int pos = pr < 22 ? f : (pr < 43 ? h : w_);
+        const float2 cs = p.cs[pos * 64 + pr];
+        const float xe = y[2 * j], xo = y[2 * j + 1];
+        y[2 * j] = xe * cs.x - xo * cs.y;
+        y[2 * j + 1] = xe * cs.y + xo * cs.x;
+      }
+    }
+  }
+  store8_bf16(ptr, y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// patchify: x[C,F,H,W] -> tokens[F*(H/2)*(W/2), C*4] bf16, column (c*2+ph)*2+pw.
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ tok,
+                                long long ldt, int C, int F, int H, int W) {
+  const int Hp = H / 2, Wp = W / 2;
+  const long long total = static_cast<long long>(F) * Hp * Wp * C * 2;  // one (c, ph) pair of pw=0,1
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // i enumerates (c, f, hp, ph, wp) with wp fastest so global reads are coalesced
+    long long t = i;
+    const int wp = t % Wp; t /= Wp;
+    const int ph = t % 2; t /= 2;
+    const int hp = t % Hp; t /= Hp;
+    const int f = t % F; t /= F;
+    const int c = static_cast<int>(t);
+    const long long src = ((static_cast<long long>(c) * F + f) * H + (hp * 2 + ph)) * W + wp * 2;
+    const float v0 = static_cast<float>(x[src]);
+    const float v1 = static_cast<float>(x[src + 1]);
+    const long long token = (static_cast<long long>(f) * Hp + hp) * Wp + wp;
+    const uint32_t packed = pack_bf16x2(v0, v1);
+    *reinterpret_cast<uint32_t*>(tok + token * ldt + (c * 2 + ph) * 2) = packed;
+  }
+}
+
+// unpatchify: y[L, 4*C] fp32 (column (ph*2+pw)*C + c) -> out[C, F, 2*Hp, 2*Wp]
+__global__ void unpatchify_kernel(const float* __restrict__ y, long long ldy,
+                                  float* __restrict__ out, int C, int F, int Hp, int Wp) {
+  const int H = Hp * 2, W = Wp * 2;
+  const long long total = static_cast<long long>(C) * F * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = i;
+    const int w = t % W; t /= W;
+    const int h = t % H; t /= H;
+    const int f = t % F; t /= F;
+    const int c = static_cast<int>(t);
+    const long long token = (static_cast<long long>(f) * Hp + (h >> 1)) * Wp + (w >> 1);
+    out[i] = y[token * ldy + ((h & 1) * 2 + (w & 1)) * C + c];
+  }
+}
+
+// sinusoidal embedding in fp64 (reference model.py:13-23): out[i, :half] = cos, [half:] = sin
+__global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int n,
+                                int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x;
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    const double freq = pow(10000.0, -static_cast<double>(j) / half);
+    const double ang = static_cast<double>(t[i]) * freq;
+    out[static_cast<long long>(i) * dim + j] = static_cast<float>(cos(ang));
+    out[static_cast<long long>(i) * dim + half + j] = static_cast<float>(sin(ang));
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ o,
+                                     long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    load8_f32(x + i * 8, v);
+    store8_bf16(o + i * 8, v);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ o,
+                                     long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    load8_bf16(x + i * 8, v);
+    store8_f32(o + i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 linear on bf16-stored weights.  64x64 output tile per CTA, 256 threads, 4x4 per thread.
+constexpr int kLT = 64, kLK = 32;
+__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ Wt,
+                  long long ldw, const __nv_bfloat16* __restrict__ bias, float* __restrict__ out,
+                  long long ldo, int M, int N, int K, int act_in, int act_out) {
+  __shared__ float sx[kLK][kLT + 1];
+  __shared__ float sw[kLK][kLT + 1];
+  const int m0 = blockIdx.y * kLT, n0 = blockIdx.x * kLT;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += kLK) {
+    // 64 rows x 32 k values each for x and W : 2048 elements / 256 threads = 8 per thread
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int idx = threadIdx.x + e * 256;
+      const int r = idx / kLK, kk = idx % kLK;
+      const int k = k0 + kk;
+      float xv = 0.f, wv = 0.f;
+      if (k < K) {
+        if (m0 + r < M) {
+          xv = x[(m0 + r) * ldx + k];
+          if (act_in == 1) xv = act_silu(xv);
+        }
+        if (n0 + r < N) wv = __bfloat162float(Wt[(n0 + r) * ldw + k]);
+      }
+      sx[kk][r] = xv;
+      sw[kk][r] = wv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kLK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sx[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sw[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += __bfloat162float(bias[n]);
+      if (act_out == 1) v = act_silu(v);
+      out[m * ldo + n] = v;
+    }
+  }
+}
+
+// modulation table: out[l, b, k, c] = float(mod[l, k, c]) + e[b, e_has_k ? k*d + c : c]
+// (reference model.py:238 `modulation + e0` per block, :286 for the head), built once per forward.
+__global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ mod,
+                                        const float* __restrict__ e, float* __restrict__ out,
+                                        int n_layers, int B, int Kk, int d, int e_has_k) {
+  const long long total = static_cast<long long>(n_layers) * B * Kk * d;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = i;
+    const int c = t % d; t /= d;
+    const int k = t % Kk; t /= Kk;
+    const int b = t % B; t /= B;
+    const int l = static_cast<int>(t);
+    const float m = __bfloat162float(mod[(static_cast<long long>(l) * Kk + k) * d + c]);
+    const float ev = e[static_cast<long long>(b) * (e_has_k ? Kk * d : d) + (e_has_k ? k * d + c : c)];
+    out[i] = m + ev;
+  }
+}
+
+}  // namespace ovb
+
+using namespace ovb;
+
+static inline int ew_grid(long long work_items, int threads) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(device_sm_count()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+extern "C" int ovb_layernorm(const ovb_ln_args* a, void* stream) {
+  OVB_CHECK_ARG(a && a->x && a->out && a->a && a->b, "ovb_layernorm: null pointer");
+  OVB_CHECK_ARG(a->rows > 0 && a->d > 0 && a->d % 8 == 0 && a->d <= 8192,
+                "ovb_layernorm: d=%d must be a multiple of 8 and <= 8192", a->d);
+  OVB_CHECK_ARG(a->ldx % 8 == 0 && a->ldo % 8 == 0, "ovb_layernorm: ld must be multiple of 8");
+  OVB_CHECK_ARG(a->mode == OVB_LN_MODULATE || a->mode == OVB_LN_AFFINE, "ovb_layernorm: bad mode");
+  OVB_CHECK_ARG(a->mode != OVB_LN_MODULATE ||
+                    (a->rows_per_sample > 0 && a->mod_row_stride % 4 == 0 &&
+                     a->mod_sample_stride % 4 == 0),
+                "ovb_layernorm: modulate needs rows_per_sample > 0 and strides %% 4 == 0");
+  LnParams p;
+  p.x = a->x; p.ldx = a->ldx; p.x_is_bf16 = a->x_is_bf16;
+  p.out = a->out; p.ldo = a->ldo; p.out_is_f32 = a->out_is_f32;
+  p.rows = a->rows; p.d = a->d; p.eps = a->eps; p.mode = a->mode;
+  p.a = a->a; p.b = a->b;
+  p.mod_row_stride = a->mod_row_stride; p.mod_sample_stride = a->mod_sample_stride;
+  p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->rows;
+  p.round_ln_bf16 = a->round_ln_bf16;
+  const int threads = ((a->d / 8 + 31) / 32) * 32;
+  layernorm_kernel<<<a->rows, threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_rmsnorm_rope(const ovb_rmsnorm_rope_args* a, void* stream) {
+  OVB_CHECK_ARG(a && a->x && a->weight, "ovb_rmsnorm_rope: null pointer");
+  OVB_CHECK_ARG(a->rows > 0 && a->d > 0 && a->d % 8 == 0 && a->d <= 8192,
+                "ovb_rmsnorm_rope: d=%d must be a multiple of 8 and <= 8192", a->d);
+  OVB_CHECK_ARG(a->ldx % 8 == 0, "ovb_rmsnorm_rope: ldx must be a multiple of 8");
+  const int col_split = a->col_split > 1 ? a->col_split : 1;
+  OVB_CHECK_ARG(a->d % col_split == 0 && (a->d / col_split) % 8 == 0,
+                "ovb_rmsnorm_rope: d/col_split must be a multiple of 8");
+  if (a->rope) {
+    OVB_CHECK_ARG(a->d % 128 == 0, "ovb_rmsnorm_rope: RoPE needs head_dim 128 (d %% 128 == 0)");
+    OVB_CHECK_ARG(a->cs_table && a->F > 0 && a->H > 0 && a->W > 0 && a->rows_per_sample > 0,
+                  "ovb_rmsnorm_rope: RoPE needs cs_table, grid sizes and rows_per_sample");
+    OVB_CHECK_ARG(a->F <= a->table_len && a->H <= a->table_len && a->W <= a->table_len,
+                  "ovb_rmsnorm_rope: grid (%d,%d,%d) exceeds table_len %d", a->F, a->H, a->W,
+                  a->table_len);
+  }
+  RmsRopeParams p;
+  p.x = reinterpret_cast<__nv_bfloat16*>(a->x); p.ldx = a->ldx;
+  p.rows = a->rows; p.d = a->d;
+  p.weight = reinterpret_cast<const __nv_bfloat16*>(a->weight);
+  p.eps = a->eps; p.rope = a->rope;
+  p.cs = reinterpret_cast<const float2*>(a->cs_table); p.table_len = a->table_len;
+  p.F = a->F; p.H = a->H; p.W = a->W;
+  p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->rows;
+  p.token_offset = a->token_offset;
+  p.cols_per_split = a->d / col_split;
+  p.col_split_stride = col_split > 1 ? a->col_split_stride : 0;
+  const int threads = ((a->d / 8 + 31) / 32) * 32;
+  rmsnorm_rope_kernel<<<a->rows, threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_patchify(const void* x, int32_t x_is_bf16, void* tokens, int64_t ldt, int32_t C,
+                            int32_t F, int32_t H, int32_t W, void* stream) {
+  OVB_CHECK_ARG(x && tokens, "ovb_patchify: null pointer");
+  OVB_CHECK_ARG(C > 0 && F > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && ldt >= C * 4 &&
+                    ldt % 2 == 0,
+                "ovb_patchify: bad shape C=%d F=%d H=%d W=%d ldt=%lld", C, F, H, W,
+                static_cast<long long>(ldt));
+  const long long total = static_cast<long long>(F) * (H / 2) * (W / 2) * C * 2;
+  const int grid = ew_grid(total, 256);
+  if (x_is_bf16)
+    patchify_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(tokens), ldt, C,
+        F, H, W);
+  else
+    patchify_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float*>(x), reinterpret_cast<__nv_bfloat16*>(tokens), ldt, C, F, H,
+        W);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_unpatchify(const float* y, int64_t ldy, float* out, int32_t C, int32_t F,
+                              int32_t Hp, int32_t Wp, void* stream) {
+  OVB_CHECK_ARG(y && out, "ovb_unpatchify: null pointer");
+  OVB_CHECK_ARG(C > 0 && F > 0 && Hp > 0 && Wp > 0 && ldy >= 4 * C, "ovb_unpatchify: bad shape");
+  const long long total = static_cast<long long>(C) * F * Hp * Wp * 4;
+  unpatchify_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, ldy, out, C, F, Hp, Wp);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_linear_f32(const float* x, int64_t ldx, const void* W, int64_t ldw,
+                              const void* bias, float* out, int64_t ldo, int32_t M, int32_t N,
+                              int32_t K, int32_t act_in, int32_t act_out, void* stream) {
+  OVB_CHECK_ARG(x && W && out, "ovb_linear_f32: null pointer");
+  OVB_CHECK_ARG(M > 0 && N > 0 && K > 0, "ovb_linear_f32: bad shape");
+  dim3 grid((N + kLT - 1) / kLT, (M + kLT - 1) / kLT);
+  linear_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw,
+      reinterpret_cast<const __nv_bfloat16*>(bias), out, ldo, M, N, K, act_in, act_out);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_sinusoidal_embedding(const float* t, float* out, int32_t n, int32_t dim,
+                                        void* stream) {
+  OVB_CHECK_ARG(t && out && n > 0 && dim > 0 && dim % 2 == 0, "ovb_sinusoidal_embedding: bad args");
+  sinusoid_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, n, dim);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_cast_f32_to_bf16(const float* x, void* out, int64_t n, void* stream) {
+  OVB_CHECK_ARG(x && out && n > 0 && n % 8 == 0, "ovb_cast_f32_to_bf16: n must be a multiple of 8");
+  cast_f32_bf16_kernel<<<ew_grid(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), n / 8);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+extern "C" int ovb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream) {
+  OVB_CHECK_ARG(x && out && n > 0 && n % 8 == 0, "ovb_cast_bf16_to_f32: n must be a multiple of 8");
+  cast_bf16_f32_kernel<<<ew_grid(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), out, n / 8);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_modulation_table(const void* mod, const float* e, float* out, int32_t n_layers,
+                                    int32_t B, int32_t K, int32_t d, int32_t e_has_k, void* stream) {
+  OVB_CHECK_ARG(mod && e && out && n_layers > 0 && B > 0 && K > 0 && d > 0,
+                "ovb_modulation_table: bad args");
+  const long long total = static_cast<long long>(n_layers) * B * K * d;
+  modulation_table_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(mod), e, out, n_layers, B, K, d, e_has_k);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}

@@ -1,0 +1,42 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting, TMA descriptor encoding
+// (cuTensorMapEncodeTiled resolved at run time so the library links without libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ovb200.h"
+
+namespace ovb {
+
+void set_last_error(const char* fmt, ...);
+
+#define OVB_CHECK_ARG(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::ovb::set_last_error(__VA_ARGS__); \
+      return OVB_ERR_INVALID_ARGUMENT;    \
+    }                                     \
+  } while (0)
+
+#define OVB_CHECK_CUDA(expr)                                                               \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::ovb::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                     \
+      return OVB_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+// bf16 tiled tensor map, 128-byte swizzle, zero fill out of bounds.
+// dims/box are innermost-first; strides_bytes has rank-1 entries (stride of dims 1..rank-1).
+int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box);
+
+int device_sm_count();
+void count_launch();
+
+}  // namespace ovb

@@ -1,0 +1,72 @@
+"""ORACLE support — generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported by oracle/ref_loader.py) on the synthetic weights/inputs of
+oracle/synth.py.  Run in the build container:   python -m oracle.gen_golden
+
+Each fixture stores only the recipe (config, seeds, shapes) and the reference's OUTPUT, so that
+tests regenerate identical weights/inputs from the seeds and compare (a) the oracle restatement in
+fp32 and (b) the CUDA path in bf16 against what the reference itself computed.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader, synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+DIT_CASES = [
+    # name, cfg overrides, latent grid (F, H, W), ctx_len, seq_len (None = exact), batch, timestep
+    dict(name="dit_tiny_a", cfg={}, grid=(3, 8, 12), ctx_len=20, seq_len=None, batch=1, t=999),
+    dict(name="dit_tiny_pad", cfg={}, grid=(2, 6, 10), ctx_len=32, seq_len=40, batch=1, t=500),
+    dict(name="dit_tiny_batch2", cfg={}, grid=(2, 8, 8), ctx_len=11, seq_len=None, batch=2, t=17),
+    dict(name="dit_tiny_4head", cfg=dict(dim=512, num_heads=4, ffn_dim=768, num_layers=1),
+         grid=(5, 8, 8), ctx_len=7, seq_len=None, batch=1, t=875),
+]
+
+
+def run_dit_case(ref, case):
+    cfg = dict(synth.TINY_DIT)
+    cfg.update(case["cfg"])
+    sd = synth.dit_state_dict(cfg, seed=1818)
+    model = ref.model.WanModel(**cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    model.eval().requires_grad_(False)
+    xs, t, ctx = synth.dit_inputs(cfg, case["grid"], case["ctx_len"], seed=7, batch=case["batch"],
+                                  timestep=case["t"])
+    Fr, H, W = case["grid"]
+    L = Fr * (H // 2) * (W // 2)
+    seq_len = case["seq_len"] or L
+    with torch.no_grad():
+        out = model(xs, t=t, context=ctx, seq_len=seq_len)
+    return cfg, seq_len, [o.numpy() for o in out]
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = ref_loader.load_reference(cpu_attention=True)
+    for case in DIT_CASES:
+        cfg, seq_len, outs = run_dit_case(ref, case)
+        meta = dict(kind="dit_forward", cfg=cfg, grid=case["grid"], ctx_len=case["ctx_len"],
+                    seq_len=seq_len, batch=case["batch"], t=case["t"], weight_seed=1818, input_seed=7,
+                    reference="omnivideo/modules/model.py WanModel.forward, fp32 CPU, "
+                              "flash_attention -> masked SDPA (oracle/ref_loader.py)")
+        path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+        np.savez_compressed(path, meta=json.dumps(meta), **{f"out{i}": o for i, o in enumerate(outs)})
+        print(f"wrote {path}: out0 shape {outs[0].shape} absmax {np.abs(outs[0]).max():.4f}")
+    if "--no-vae" not in sys.argv:
+        try:
+            from oracle import gen_golden_vae
+            gen_golden_vae.main(ref)
+        except ImportError:
+            pass
+
+
+if __name__ == "__main__":
+    main()

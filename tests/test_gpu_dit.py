@@ -1,0 +1,113 @@
+"""Whole-forward parity of the B200 WanModel:
+  * against the committed goldens (outputs of the reference itself, fp32) within the north-star
+    tolerance for the bf16 path: per-step latent rel-L2 <= 1e-2;
+  * against the bf16-emulating oracle on the same seeded inputs (tighter: <= 5e-3);
+  * drop-in properties: reference state-dict names load strictly, flash_attention() keeps the
+    reference's dtype contract.
+"""
+import pytest
+import torch
+
+from oracle import dit as O
+from oracle import synth
+from tests.golden_util import dit_case, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def _build(cfg, sd):
+    from omni_video_b200.modules.model import WanModel
+    model = WanModel(**cfg, skip_init=True)
+    model.load_state_dict(sd, strict=True)     # reference parameter names, strict
+    return model.to(bf16).cuda().eval()        # like x2x_gen_unified.py:126
+
+
+@pytest.mark.parametrize("name", golden_names("dit_forward"))
+def test_dit_forward_vs_reference_golden(name):
+    meta, gold = load_golden(name)
+    cfg, sd, xs, t, ctx, seq_len = dit_case(meta)
+    model = _build(cfg, sd)
+    outs = model([x.cuda() for x in xs], t=t.cuda(), context=[c.cuda() for c in ctx], seq_len=seq_len)
+    torch.cuda.synchronize()
+    assert len(outs) == len(gold)
+    for o, g in zip(outs, gold):
+        assert o.dtype == torch.float32 and o.shape == g.shape
+        err = O.rel_l2(o.cpu(), g)
+        assert err <= 1e-2, f"{name}: rel-L2 vs reference {err}"   # BASELINE.json north_star tolerance
+
+
+@pytest.mark.parametrize("name", golden_names("dit_forward")[:3])
+def test_dit_forward_vs_bf16_oracle(name):
+    meta, _ = load_golden(name)
+    cfg, sd, xs, t, ctx, seq_len = dit_case(meta)
+    model = _build(cfg, sd)
+    xs_b = [x.to(bf16) for x in xs]
+    ctx_b = [c.to(bf16) for c in ctx]
+    outs = model([x.cuda() for x in xs_b], t=t.cuda(), context=[c.cuda() for c in ctx_b], seq_len=seq_len)
+    ref = O.dit_forward(synth.round_bf16(sd), cfg, [x.float() for x in xs_b], t,
+                        [c.float() for c in ctx_b], seq_len, emulate_bf16=True)
+    for o, r in zip(outs, ref):
+        err = O.rel_l2(o.cpu(), r)
+        assert err <= 5e-3, f"{name}: rel-L2 vs bf16 oracle {err}"
+
+
+def test_dit_medium_vs_bf16_oracle():
+    """4 heads, 3 layers, 2340 tokens (not a multiple of the 128/256 tile sizes), padded seq_len."""
+    cfg = dict(synth.TINY_DIT, dim=512, num_heads=4, ffn_dim=1024, num_layers=3, text_len=64)
+    sd = synth.dit_state_dict(cfg, seed=3)
+    xs, t, ctx = synth.dit_inputs(cfg, (5, 36, 52), 40, seed=4, timestep=321)
+    seq_len = 5 * 18 * 26 + 12
+    model = _build(cfg, sd)
+    xs_b, ctx_b = [x.to(bf16) for x in xs], [c.to(bf16) for c in ctx]
+    out = model([x.cuda() for x in xs_b], t=t.cuda(), context=[c.cuda() for c in ctx_b], seq_len=seq_len)[0]
+    ref = O.dit_forward(synth.round_bf16(sd), cfg, [x.float() for x in xs_b], t,
+                        [c.float() for c in ctx_b], seq_len, emulate_bf16=True)[0]
+    assert O.rel_l2(out.cpu(), ref) <= 5e-3
+
+
+def test_forward_is_deterministic_and_batch_consistent():
+    """same input twice -> bit-identical; a batch of two equals two single calls."""
+    meta, _ = load_golden("dit_tiny_batch2")
+    cfg, sd, xs, t, ctx, seq_len = dit_case(meta)
+    model = _build(cfg, sd)
+    xc, cc, tc = [x.cuda() for x in xs], [c.cuda() for c in ctx], t.cuda()
+    a = model(xc, t=tc, context=cc, seq_len=seq_len)
+    b = model(xc, t=tc, context=cc, seq_len=seq_len)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    for i in range(2):
+        single = model([xc[i]], t=tc[i:i + 1], context=[cc[i]], seq_len=seq_len)[0]
+        assert torch.equal(single, a[i])
+
+
+def test_flash_attention_dropin_contract():
+    """reference attention.py:24-133: output in q's input dtype, k_lens masking, CUDA assert."""
+    from omni_video_b200.modules.attention import flash_attention
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(2, 200, 2, 128, generator=g)
+    k = torch.randn(2, 150, 2, 128, generator=g)
+    v = torch.randn(2, 150, 2, 128, generator=g)
+    out = flash_attention(q.cuda(), k.cuda(), v.cuda(), k_lens=torch.tensor([150, 90]))
+    assert out.dtype == torch.float32 and out.shape == (2, 200, 2, 128)
+    for b, kl in enumerate((150, 90)):
+        ref = O.attention(q[b].bfloat16().float(), k[b].bfloat16().float(), v[b].bfloat16().float(),
+                          kl, emulate=True)
+        assert O.rel_l2(out[b].cpu(), ref) < 6e-3
+    out16 = flash_attention(q.cuda().to(bf16), k.cuda().to(bf16), v.cuda().to(bf16))
+    assert out16.dtype == bf16
+    with pytest.raises(AssertionError):
+        flash_attention(q, k, v)  # CPU tensors: same assert as the reference (:54)
+    with pytest.raises(NotImplementedError):
+        flash_attention(q.cuda(), k.cuda(), v.cuda(), causal=True)
+
+
+def test_module_granular_hooks_match_engine():
+    """block-level API (what a reference-style monkey patch calls) agrees with the fused engine."""
+    meta, _ = load_golden("dit_tiny_a")
+    cfg, sd, xs, t, ctx, seq_len = dit_case(meta)
+    model = _build(cfg, sd)
+    out_engine = model([x.cuda() for x in xs], t=t.cuda(), context=[c.cuda() for c in ctx], seq_len=seq_len)[0]
+    from omni_video_b200.modules.reference_style import forward_module_granular
+    out_mod = forward_module_granular(model, [x.cuda() for x in xs], t.cuda(), [c.cuda() for c in ctx], seq_len)[0]
+    assert O.rel_l2(out_mod.cpu(), out_engine.cpu()) < 5e-3
