@@ -21,6 +21,28 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Optional per-launch timing (bench.py's roofline leg): when `timeline` is a list, gemm() and
+# attention() bracket their launch with CUDA events on the launching stream and append
+# (kind, algorithmic FLOPs, shape, start_event, end_event).  None (the default) costs nothing.
+timeline = None
+
+
+def _tl_begin():
+    if timeline is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _tl_end(ev, kind, flops, shape):
+    if ev is None:
+        return
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    timeline.append((kind, flops, shape, ev, end))
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -98,7 +120,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, epil
         args.rows_per_sample = rps
     args.n_split, args.out_split_stride = n_split, out_split_stride
     args.k_split, args.a_split_stride = k_split, a_split_stride
+    ev = _tl_begin()
     _lib.check(lib.ovb_gemm_bf16(C.byref(args), _stream()), "ovb_gemm_bf16")
+    _tl_end(ev, "gemm", 2.0 * M * N * K, (M, N, K))
     return out
 
 
@@ -134,7 +158,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
         arr = (C.c_int32 * B)(*kl)
         args.k_lens = C.cast(arr, C.POINTER(C.c_int32))
     args.softmax_scale = float(softmax_scale) if softmax_scale is not None else 0.0
+    ev = _tl_begin()
     _lib.check(lib.ovb_attn_fwd(C.byref(args), _stream()), "ovb_attn_fwd")
+    if ev is not None:
+        keys = sum(int(x) for x in k_lens) if k_lens is not None else B * Lk
+        _tl_end(ev, "attn", 4.0 * Lq * keys * H * D, (B, H, Lq, Lk))
     return out
 
 
