@@ -25,11 +25,11 @@ fi
 if has ncu; then
   CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
   $CMD > gpurun_out/plain.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 1200 --csv \
       --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
   echo "ncu list rc=$?"
   $CMD > gpurun_out/plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd|gemm_bf16' -s 3 -c 9 \
+  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'attn_fwd|gemm_bf16' -c 9 \
       -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
 fi

@@ -1,0 +1,78 @@
+"""Sequence-parallel parity on real GPUs (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/sp_check.py
+
+Every rank runs (a) the single-GPU forward of a small DiT and (b) the Ulysses forward over all ranks
+(engine path: GEMM epilogues write the all-to-all layouts; and the reference-style per-module hooks
+`sp_attn_forward` / `sp_cross_attn_forward` / `sp_dit_forward`), and checks (b) against (a).
+"""
+import os
+import sys
+import types
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from omni_video_b200.distributed.full_sequence_parallel import (sp_attn_forward,  # noqa: E402
+                                                                sp_cross_attn_forward, sp_dit_forward)
+from omni_video_b200.distributed.util import init_sequence_parallel_group  # noqa: E402
+from omni_video_b200.modules.model import WanModel  # noqa: E402
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    heads = 8 if world in (2, 4, 8) else 2 * world
+    cfg = dict(model_type="t2v", patch_size=(1, 2, 2), text_len=64, in_dim=16, dim=128 * heads,
+               ffn_dim=1024, freq_dim=256, text_dim=256, out_dim=16, num_heads=heads, num_layers=2,
+               window_size=(-1, -1), qk_norm=True, cross_attn_norm=True, eps=1e-6)
+    torch.manual_seed(1818)  # same weights on every rank
+    model = WanModel(**cfg).to(dev)
+    torch.nn.init.normal_(model.head.head.weight, std=0.02)
+    for p in model.parameters():
+        if p.dim() == 1:
+            p.data.add_(torch.randn_like(p) * 0.02)
+    model = model.to(torch.bfloat16).eval().requires_grad_(False)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = [torch.randn(16, 3, 16, 22, generator=gen, device=dev)]           # 3*8*11 = 264 tokens
+    ctx = [torch.randn(40, 256, generator=gen, device=dev).to(torch.bfloat16)]
+    t = torch.tensor([500], device=dev)
+    L = 264
+    seq_len = ((L + world - 1) // world) * world + world                   # forces a padded tail
+    ref = model(x, t=t, context=ctx, seq_len=seq_len)[0]
+
+    g = init_sequence_parallel_group(world)
+    model.sp_group = g
+    out_engine = model(x, t=t, context=ctx, seq_len=seq_len)[0]
+    e1 = rel_l2(out_engine, ref)
+
+    for blk in model.blocks:
+        blk.self_attn.sp_group = g
+        blk.cross_attn.sp_group = g
+        blk.self_attn.forward = types.MethodType(sp_attn_forward, blk.self_attn)
+        blk.cross_attn.forward = types.MethodType(sp_cross_attn_forward, blk.cross_attn)
+    model.forward = types.MethodType(sp_dit_forward, model)
+    out_hooks = model(x, t=t, context=ctx, seq_len=seq_len)[0]
+    e2 = rel_l2(out_hooks, ref)
+    torch.cuda.synchronize()
+    print(f"[rank {rank}/{world}] ulysses engine vs single-GPU rel-L2 {e1:.3e}; reference-style hooks {e2:.3e}",
+          flush=True)
+    ok = e1 <= 2e-3 and e2 <= 5e-3 and bool(torch.isfinite(out_engine).all())
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

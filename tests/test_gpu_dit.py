@@ -5,6 +5,8 @@
   * drop-in properties: reference state-dict names load strictly, flash_attention() keeps the
     reference's dtype contract.
 """
+import os
+
 import pytest
 import torch
 
@@ -111,3 +113,19 @@ def test_module_granular_hooks_match_engine():
     from omni_video_b200.modules.reference_style import forward_module_granular
     out_mod = forward_module_granular(model, [x.cuda() for x in xs], t.cuda(), [c.cuda() for c in ctx], seq_len)[0]
     assert O.rel_l2(out_mod.cpu(), out_engine.cpu()) < 5e-3
+
+
+@pytest.mark.gpu
+def test_ulysses_two_gpus_matches_single_gpu():
+    """Runs scripts/sp_check.py under torchrun when the box has >= 2 GPUs (the driver's GPU tier is
+    normally one GPU: then the host-side logic is covered by tests/test_distributed_cpu.py)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "scripts", "sp_check.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
