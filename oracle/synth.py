@@ -87,3 +87,101 @@ def dit_inputs(cfg: dict, grid_lat: Tuple[int, int, int], ctx_len: int, seed: in
 
 def round_bf16(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return {k: v.to(torch.bfloat16).to(torch.float32) for k, v in sd.items()}
+
+
+# ------------------------------------------------------------------------------------------ VAE
+def vae_state_dict(seed: int = 1818, dim: int = 96, z_dim: int = 16) -> Dict[str, torch.Tensor]:
+    """fp32 state dict with the parameter names/shapes of the reference's `WanVAE_` for the one
+    configuration the pipeline instantiates (vae2_1.py:596-603: dim 96, dim_mult [1,2,4,4], two
+    res blocks, temperal_downsample [False, True, True]).  Weights ~ N(0, 1/fan_in) so activations
+    stay O(1) through ~30 convs; the zero-initialised attention `proj.weight` (vae2_1.py:237) gets
+    real values."""
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, co, ci, *k, gain=1.0):
+        fan_in = ci * int(np.prod(k))
+        sd[name + ".weight"] = _normal(rng, (co, ci) + tuple(k), gain / math.sqrt(fan_in))
+        sd[name + ".bias"] = _normal(rng, (co,), 0.02)
+
+    def gamma(name, c, images=False):
+        sd[name + ".gamma"] = (1.0 + _normal(rng, (c,), 0.05)).reshape((c, 1, 1) if images else (c, 1, 1, 1))
+
+    def res(p, ci, co):
+        gamma(p + "residual.0", ci)
+        conv(p + "residual.2", co, ci, 3, 3, 3)
+        gamma(p + "residual.3", co)
+        conv(p + "residual.6", co, co, 3, 3, 3, gain=0.5)
+        if ci != co:
+            conv(p + "shortcut", co, ci, 1, 1, 1)
+
+    def attn(p, c):
+        gamma(p + "norm", c, images=True)
+        conv(p + "to_qkv", 3 * c, c, 1, 1)
+        conv(p + "proj", c, c, 1, 1, gain=0.5)
+
+    # ---- encoder (vae2_1.py:264-315)
+    dims = [dim * u for u in (1, 1, 2, 4, 4)]
+    conv("encoder.conv1", dims[0], 3, 3, 3, 3)
+    j = 0
+    t_down = [False, True, True]
+    for i, (ci, co) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(2):
+            res(f"encoder.downsamples.{j}.", ci, co)
+            ci = co
+            j += 1
+        if i != 3:
+            conv(f"encoder.downsamples.{j}.resample.1", co, co, 3, 3)
+            if t_down[i]:
+                conv(f"encoder.downsamples.{j}.time_conv", co, co, 3, 1, 1)
+            j += 1
+    res("encoder.middle.0.", dims[-1], dims[-1])
+    attn("encoder.middle.1.", dims[-1])
+    res("encoder.middle.2.", dims[-1], dims[-1])
+    gamma("encoder.head.0", dims[-1])
+    conv("encoder.head.2", z_dim * 2, dims[-1], 3, 3, 3)
+    conv("conv1", z_dim * 2, z_dim * 2, 1, 1, 1)
+    conv("conv2", z_dim, z_dim, 1, 1, 1)
+    # ---- decoder (vae2_1.py:368-420)
+    ddims = [dim * u for u in (4, 4, 4, 2, 1)]
+    conv("decoder.conv1", ddims[0], z_dim, 3, 3, 3)
+    res("decoder.middle.0.", ddims[0], ddims[0])
+    attn("decoder.middle.1.", ddims[0])
+    res("decoder.middle.2.", ddims[0], ddims[0])
+    j = 0
+    t_up = [True, True, False]
+    for i, (ci, co) in enumerate(zip(ddims[:-1], ddims[1:])):
+        if i in (1, 2, 3):
+            ci = ci // 2
+        for _ in range(3):
+            res(f"decoder.upsamples.{j}.", ci, co)
+            ci = co
+            j += 1
+        if i != 3:
+            conv(f"decoder.upsamples.{j}.resample.1", co // 2, co, 3, 3)
+            if t_up[i]:
+                conv(f"decoder.upsamples.{j}.time_conv", co * 2, co, 3, 1, 1)
+            j += 1
+    gamma("decoder.head.0", ddims[-1])
+    conv("decoder.head.2", 3, ddims[-1], 3, 3, 3)
+    return sd
+
+
+def vae_latent(grid: Tuple[int, int, int], seed: int = 7) -> torch.Tensor:
+    """Normalised latent z [16, T, h, w] ~ N(0,1) (what the sampler hands to decode)."""
+    rng = np.random.default_rng(seed)
+    return _normal(rng, (16,) + tuple(grid), 1.0)
+
+
+def vae_video(shape: Tuple[int, int, int], seed: int = 7) -> torch.Tensor:
+    """Smooth synthetic video [3, T, H, W] in [-1, 1]: low-frequency sinusoids + 0.05 noise
+    (SURVEY.md §8(d) config 5)."""
+    rng = np.random.default_rng(seed)
+    T, H, W = shape
+    t = torch.arange(T, dtype=torch.float32).view(1, T, 1, 1)
+    y = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1)
+    x = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    ph = torch.from_numpy(rng.uniform(0, 6.28, size=(3, 1, 1, 1)).astype(np.float32))
+    v = 0.5 * torch.sin(0.11 * x + 0.07 * y + 0.3 * t + ph) + 0.3 * torch.cos(0.05 * x - 0.13 * y + ph)
+    v = v + 0.05 * _normal(rng, (3, T, H, W), 1.0)
+    return v.clamp(-1, 1)
