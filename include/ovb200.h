@@ -53,6 +53,7 @@ int64_t ovb_launch_count(void);
  *   OVB_EPI_RESID_F32       out(fp32)  = resid + bf16(acc + bias)                  (model.py:250)
  *   OVB_EPI_GATE_RESID_F32  out(fp32)  = resid + bf16(acc + bias) * gate           (model.py:246,254)
  *   OVB_EPI_F32             out(fp32)  = acc + bias
+ *   OVB_EPI_RESID_BF16      out(bf16)  = resid(bf16) + bf16(acc + bias)            (vae2_1.py:258-261)
  *
  * gate is fp32; element (row r, col n) is read at
  *   gate[(r / rows_per_sample) * gate_sample_stride + (r % rows_per_sample) * gate_row_stride + n]
@@ -71,6 +72,7 @@ int64_t ovb_launch_count(void);
 #define OVB_EPI_RESID_F32 2
 #define OVB_EPI_GATE_RESID_F32 3
 #define OVB_EPI_F32 4
+#define OVB_EPI_RESID_BF16 5
 
 typedef struct ovb_gemm_args {
   const void* A;      /* bf16 [M, K] (or k_split x [M, K/k_split]) */
@@ -82,7 +84,7 @@ typedef struct ovb_gemm_args {
   int64_t ldo;
   int32_t M, N, K;
   int32_t epilogue;
-  const void* resid;  /* fp32 [M, N], ld = ldr (RESID / GATE_RESID); may alias out */
+  const void* resid;  /* fp32 [M, N], ld = ldr (RESID / GATE_RESID), bf16 for RESID_BF16; may alias out */
   int64_t ldr;
   const void* gate;   /* fp32, see above (GATE_RESID) */
   int64_t gate_row_stride;
@@ -209,6 +211,71 @@ int ovb_modulation_table(const void* mod, const float* e, float* out, int32_t n_
 /* fp32 -> bf16 / bf16 -> fp32 casts of n contiguous elements (n % 8 == 0). */
 int ovb_cast_f32_to_bf16(const float* x, void* out, int64_t n, void* stream);
 int ovb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
+
+/* ==== Wan2.1 causal-3D VAE (reference omnivideo/modules/vae2_1.py) ================================
+ * Activations are channels-last bf16 [T, H, W, C] (C a multiple of 16); all frames of a clip are
+ * processed in one pass (the reference's chunk loop + feat_cache, vae2_1.py:515-567, is causal zero
+ * padding: DESIGN.md §6).
+ *
+ * ---- implicit-GEMM convolution (tcgen05 / TMEM / TMA) ------------------------------------------
+ * out[t,h,w,n] = bias[n] + sum_{tap,c} x[t*st + dt[tap], h*sh + dh[tap], w*sw + dw[tap], c]
+ *                                       * w[n, tap*Cin + c]    (+ resid[t,h,w,n])
+ * Reads outside x contribute zero (TMA zero fill) — that is the zero padding of CausalConv3d
+ * (vae2_1.py:16-35: W/H symmetric, T on the left only), of nn.Conv2d(padding=1) (:78,:82) and of
+ * ZeroPad2d((0,1,0,1)) (:88,:92).  Replaces every cuDNN conv of the VAE.
+ * Output element (t,h,w,n), OVB_CONV_OUT_BF16:
+ *     out[out_base + t*os_t + h*os_h + w*os_w + (n / n_group)*group_stride + n % n_group]
+ *   (n_group = 0: no grouping).  Doubled os_h/os_w + a phase offset in out_base writes one phase of a
+ *   2x nearest-upsampled image (Upsample + Conv2d, :75-84, as four 2x2 convs); n_group = C with
+ *   group_stride = os_t interleaves time_conv's two channel halves as consecutive frames (:133-136).
+ * OVB_CONV_OUT_F32_PLANAR(_CLAMP): fp32 out[n*plane_stride + out_base + t*os_t + h*os_h + w*os_w],
+ *   optionally clamped to [-1,1] (Wan2_1_VAE.decode, :660).
+ */
+#define OVB_CONV_OUT_BF16 0
+#define OVB_CONV_OUT_F32_PLANAR 1
+#define OVB_CONV_OUT_F32_PLANAR_CLAMP 2
+
+typedef struct ovb_conv3d_args {
+  const void* x;          /* bf16 [Ti, Hi, Wi, Cin] */
+  int32_t Ti, Hi, Wi, Cin;
+  const void* w;          /* bf16 [w_rows, n_taps*Cin], rows >= Cout are zero */
+  int32_t w_rows;
+  const float* bias;      /* fp32 [Cout] or NULL */
+  int32_t Cout;
+  int32_t n_taps;         /* <= 27 */
+  const int8_t* tap_dt;   /* HOST arrays [n_taps] */
+  const int8_t* tap_dh;
+  const int8_t* tap_dw;
+  int32_t st, sh, sw;     /* input step per output step (1 or 2) */
+  int32_t To, Ho, Wo;     /* output extents */
+  void* out;
+  int64_t os_t, os_h, os_w, out_base;   /* in elements */
+  int32_t n_group;
+  int64_t group_stride;
+  const void* resid;      /* bf16, addressed like out, or NULL */
+  int32_t out_mode;
+  int64_t plane_stride;
+} ovb_conv3d_args;
+
+int ovb_conv3d(const ovb_conv3d_args* args, void* stream);
+
+/* RMS_norm over channels (+ optional SiLU) on channels-last voxels (vae2_1.py:38-53, :194-196):
+ * out[v, c] = act( x[v, c] / max(||x[v, :]||_2, 1e-12) * sqrt(C) * gamma[c] ).  HBM-bound: 4 B/elem. */
+int ovb_rmsnorm_silu_cl(const void* x, const float* gamma, void* out, int64_t n_vox, int32_t C,
+                        int32_t silu, void* stream);
+
+/* Layout converters with a per-channel affine (latent de/normalisation, vae2_1.py:535-539,:546-550):
+ * planar_to_cl: out[i, c] (bf16, c < Cpad) = c < C ? src[c*n + i]*scale[c] + shift[c] : 0
+ * cl_to_planar: out[c*n + i] (fp32, c < C)  = float(src[i*Cs + c])*scale[c] + shift[c]      */
+int ovb_planar_to_cl(const float* src, const float* scale, const float* shift, void* out, int32_t C,
+                     int32_t Cpad, int64_t n, void* stream);
+int ovb_cl_to_planar(const void* src, int32_t Cs, const float* scale, const float* shift, float* out,
+                     int32_t C, int64_t n, void* stream);
+
+/* Row softmax for the VAE's single-head attention (vae2_1.py:251): P[r, :] = softmax(scale*S[r, :]),
+ * S fp32 [rows, cols] (ld lds) -> P bf16 (ld ldp). */
+int ovb_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int32_t rows, int32_t cols,
+                     float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libovb200.so")
 OVB_OK = 0
 
 # epilogues / modes (mirror include/ovb200.h)
-EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_GATE_RESID_F32, EPI_F32 = range(5)
+EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_GATE_RESID_F32, EPI_F32, EPI_RESID_BF16 = range(6)
+CONV_OUT_BF16, CONV_OUT_F32_PLANAR, CONV_OUT_F32_PLANAR_CLAMP = range(3)
 LN_MODULATE, LN_AFFINE = 0, 1
 
 
@@ -75,6 +76,24 @@ class RmsRopeArgs(C.Structure):
     ]
 
 
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("Ti", C.c_int32), ("Hi", C.c_int32), ("Wi", C.c_int32), ("Cin", C.c_int32),
+        ("w", C.c_void_p), ("w_rows", C.c_int32),
+        ("bias", C.c_void_p),
+        ("Cout", C.c_int32), ("n_taps", C.c_int32),
+        ("tap_dt", C.POINTER(C.c_int8)), ("tap_dh", C.POINTER(C.c_int8)), ("tap_dw", C.POINTER(C.c_int8)),
+        ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("To", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("out", C.c_void_p),
+        ("os_t", C.c_int64), ("os_h", C.c_int64), ("os_w", C.c_int64), ("out_base", C.c_int64),
+        ("n_group", C.c_int32), ("group_stride", C.c_int64),
+        ("resid", C.c_void_p),
+        ("out_mode", C.c_int32), ("plane_stride", C.c_int64),
+    ]
+
+
 # symbol -> (restype, argtypes); every symbol declared in include/ovb200.h must be listed here
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 _SIGNATURES = {
@@ -97,6 +116,15 @@ _SIGNATURES = {
                                            C.c_void_p]),
     "ovb_modulation_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "ovb_conv3d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "ovb_rmsnorm_silu_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                      C.c_int32, C.c_void_p]),
+    "ovb_planar_to_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                   C.c_int32, C.c_int64, C.c_void_p]),
+    "ovb_cl_to_planar": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_int64, C.c_void_p]),
+    "ovb_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                   C.c_float, C.c_void_p]),
     "ovb_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ovb_cast_bf16_to_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }

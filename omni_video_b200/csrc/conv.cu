@@ -1,0 +1,389 @@
+// ovb_conv3d: implicit-GEMM convolution over channels-last video tensors for sm_100a.
+//
+//   out[t, h, w, n] = bias[n] + sum_{tap, c} x[t*st + dt(tap), h*sh + dh(tap), w*sw + dw(tap), c]
+//                                            * W[n, tap*Cin + c]            (+ resid[t, h, w, n])
+//
+// This is the CausalConv3d / Conv2d workhorse of the Wan2.1 VAE (reference
+// omnivideo/modules/vae2_1.py:16-35, :75-95).  GEMM view: M = output voxels, N = Cout,
+// K = taps * Cin.  An M tile is a bw x bh box of 128 output voxels of one frame; for every tap the
+// A operand of that tile is the SAME box shifted by (dt, dh, dw), so the producer warp fetches it
+// with one 4-D TMA box load per (tap, channel chunk) straight from the activation tensor — no
+// im2col buffer, and TMA's zero fill outside the tensor IS the spatial zero padding and the
+// causal (left-only) temporal padding.  The box lands in shared memory as 128 rows x KC channels,
+// K-major with the hardware swizzle, i.e. exactly the tcgen05.mma A-operand layout.
+//
+// Same warp-specialised persistent structure as gemm.cu (TMA producer warp, single-thread MMA
+// issuer, TMEM allocator warp, 4 epilogue warps; two TMEM accumulators so the epilogue of tile i
+// overlaps the main loop of tile i+1); tile width BN, channel chunk KC (64/32/16 -> 128/64/32-byte
+// swizzle) and the ring depth are runtime parameters so one kernel serves every layer of the VAE
+// (Cin, Cout in {16, 32, 96, 192, 384, 768} and the 3-channel head).
+//
+// The output address of voxel (t, h, w), channel n is
+//     out_base + t*os_t + h*os_h + w*os_w + (n / n_group)*group_stride + (n % n_group)
+// which lets the same kernel (a) write a 2x nearest-upsampled phase (os_h, os_w doubled, one launch
+// per phase with phase-specific 2x2 taps) and (b) interleave the two channel halves of
+// upsample3d's time_conv as consecutive frames (vae2_1.py:133-136).
+#include <string.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace ovb {
+
+constexpr int kConvThreads = 256;
+constexpr int kConvMaxStages = 8;
+constexpr int kConvMaxTaps = 27;
+constexpr int kConvSmemBudget = 225 * 1024;
+
+struct ConvParams {
+  int To, Ho, Wo;
+  int bw_log2, bh;   // box: (1 << bw_log2) x bh == 128 voxels
+  int n_wt, n_ht;
+  int st, sh, sw;
+  int Cin, KC, n_kc;
+  int n_taps;
+  int Cout, BN, n_nt;
+  int stages, stage_bytes, a_bytes;
+  const float* bias;
+  void* out;
+  const __nv_bfloat16* resid;
+  long long os_t, os_h, os_w, out_base;
+  int n_group;
+  long long group_stride;
+  int out_mode;
+  long long plane_stride;
+  signed char dt[kConvMaxTaps], dh[kConvMaxTaps], dw[kConvMaxTaps];
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + kConvMaxStages;
+  uint64_t* tfull_bar = empty_bar + kConvMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = p.To * p.n_ht * p.n_wt;
+  const int num_tiles = m_tiles * p.n_nt;
+  const int num_ks = p.n_taps * p.n_kc;
+  const int bw = 1 << p.bw_log2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = static_cast<uint32_t>(128 * p.KC * 2 + p.BN * p.KC * 2);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_nt;
+        int m = tile / p.n_nt;
+        const int wt = m % p.n_wt;
+        m /= p.n_wt;
+        const int ht = m % p.n_ht;
+        const int t = m / p.n_ht;
+        const int w0 = (wt << p.bw_log2) * p.sw, h0 = ht * p.bh * p.sh, t0 = t * p.st;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          const int ct = t0 + p.dt[tap], ch = h0 + p.dh[tap], cw = w0 + p.dw[tap];
+          for (int kc = 0; kc < p.n_kc; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * p.stage_bytes;
+            uint8_t* sb = sa + p.a_bytes;
+            mbar_expect_tx(&full_bar[stage], tx);
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * p.KC, cw, ch, ct);
+            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + kc * p.KC, nt * p.BN);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t row_bytes = p.KC * 2;
+      const int k_steps = p.KC / 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int ks = 0; ks < num_ks; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
+          const uint32_t sb = sa + p.a_bytes;
+          for (int k = 0; k < k_steps; ++k) {
+            umma_ss(d_tmem, umma_desc_kmajor(sa + k * 32, row_bytes),
+                    umma_desc_kmajor(sb + k * 32, row_bytes), idesc, (ks | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (ks == num_ks - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // accumulator row = voxel inside the box
+    const int hl = r >> p.bw_log2, wl = r & (bw - 1);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_nt;
+      int m = tile / p.n_nt;
+      const int wt = m % p.n_wt;
+      m /= p.n_wt;
+      const int ht = m % p.n_ht;
+      const int t = m / p.n_ht;
+      const int h = ht * p.bh + hl, w = (wt << p.bw_log2) + wl;
+      const bool ok = h < p.Ho && w < p.Wo;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const long long vox = p.out_base + t * p.os_t + h * p.os_h + w * p.os_w;
+      const int n_chunks = p.BN / 16;
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        const int n0 = nt * p.BN + c * 16;
+        if (n0 >= p.Cout) break;  // warp-uniform
+        uint32_t v[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + c * 16, v);
+        tmem_wait_ld();
+        if (ok) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + j < p.Cout) f[j] += __ldg(p.bias + n0 + j);
+        }
+        if (p.out_mode == OVB_CONV_OUT_BF16) {
+          const int grp = p.n_group > 0 ? n0 / p.n_group : 0;
+          const long long off = vox + grp * p.group_stride + (n0 - grp * p.n_group);
+          if (p.resid != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + off);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint4 rv = rp[g];
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 a = __bfloat1622float2(r2[j]);
+                // conv result is stored as bf16 before the add in the unfused formulation
+                f[g * 8 + 2 * j] = bf16_round(f[g * 8 + 2 * j]) + a.x;
+                f[g * 8 + 2 * j + 1] = bf16_round(f[g * 8 + 2 * j + 1]) + a.y;
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 o;
+            o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+            o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+            o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+            o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+            op[g] = o;
+          }
+        } else {  // OVB_CONV_OUT_F32_PLANAR(_CLAMP): out[n][t][h][w]
+          float* op = reinterpret_cast<float*>(p.out) + vox;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (n0 + j < p.Cout) {
+              float y = f[j];
+              if (p.out_mode == OVB_CONV_OUT_F32_PLANAR_CLAMP) y = fminf(fmaxf(y, -1.0f), 1.0f);
+              op[(n0 + j) * p.plane_stride] = y;
+            }
+          }
+        }
+        }  // ok
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace ovb
+
+extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(a != nullptr, "ovb_conv3d: null args");
+  OVB_CHECK_ARG(a->x && a->w && a->out, "ovb_conv3d: null x/w/out");
+  OVB_CHECK_ARG(a->Ti > 0 && a->Hi > 0 && a->Wi > 0 && a->To > 0 && a->Ho > 0 && a->Wo > 0,
+                "ovb_conv3d: bad extents in [%d,%d,%d] out [%d,%d,%d]", a->Ti, a->Hi, a->Wi, a->To,
+                a->Ho, a->Wo);
+  OVB_CHECK_ARG(a->Cin > 0 && a->Cin % 16 == 0, "ovb_conv3d: Cin=%d must be a multiple of 16", a->Cin);
+  OVB_CHECK_ARG(a->Cout > 0 && a->w_rows >= a->Cout && a->w_rows % 16 == 0,
+                "ovb_conv3d: Cout=%d w_rows=%d (w_rows must be >= Cout and a multiple of 16)", a->Cout,
+                a->w_rows);
+  OVB_CHECK_ARG(a->n_taps >= 1 && a->n_taps <= kConvMaxTaps && a->tap_dt && a->tap_dh && a->tap_dw,
+                "ovb_conv3d: n_taps=%d outside [1,%d] or null tap arrays", a->n_taps, kConvMaxTaps);
+  OVB_CHECK_ARG(a->st >= 1 && a->sh >= 1 && a->sw >= 1 && a->st <= 2 && a->sh <= 2 && a->sw <= 2,
+                "ovb_conv3d: strides must be 1 or 2");
+  OVB_CHECK_ARG(a->out_mode >= OVB_CONV_OUT_BF16 && a->out_mode <= OVB_CONV_OUT_F32_PLANAR_CLAMP,
+                "ovb_conv3d: unknown out_mode %d", a->out_mode);
+  OVB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w) |
+                 reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->resid)) % 16 == 0,
+                "ovb_conv3d: pointers must be 16-byte aligned");
+  if (a->out_mode == OVB_CONV_OUT_BF16) {
+    OVB_CHECK_ARG(a->Cout % 16 == 0, "ovb_conv3d: bf16 output needs Cout %% 16 == 0 (got %d)", a->Cout);
+    OVB_CHECK_ARG(a->os_t % 8 == 0 && a->os_h % 8 == 0 && a->os_w % 8 == 0 && a->out_base % 8 == 0 &&
+                      a->group_stride % 8 == 0,
+                  "ovb_conv3d: bf16 output strides must be multiples of 8 elements");
+    OVB_CHECK_ARG(a->n_group == 0 || (a->n_group % 16 == 0 && a->Cout % a->n_group == 0),
+                  "ovb_conv3d: n_group=%d must be a multiple of 16 dividing Cout", a->n_group);
+  } else {
+    OVB_CHECK_ARG(a->resid == nullptr && a->n_group == 0,
+                  "ovb_conv3d: planar fp32 output supports neither resid nor channel groups");
+  }
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.To = a->To; p.Ho = a->Ho; p.Wo = a->Wo;
+  p.st = a->st; p.sh = a->sh; p.sw = a->sw;
+  // ---- M tile shape: bw x bh = 128 voxels with the least padding waste
+  {
+    long long best = -1;
+    for (int l2 = 7; l2 >= 3; --l2) {
+      const int bw = 1 << l2, bh = 128 >> l2;
+      const long long cover = static_cast<long long>((a->Wo + bw - 1) / bw) * bw *
+                              ((a->Ho + bh - 1) / bh) * bh;
+      if (best < 0 || cover < best) {
+        best = cover;
+        p.bw_log2 = l2;
+        p.bh = bh;
+      }
+    }
+  }
+  const int bw = 1 << p.bw_log2;
+  p.n_wt = (a->Wo + bw - 1) / bw;
+  p.n_ht = (a->Ho + p.bh - 1) / p.bh;
+  // ---- K chunk
+  p.Cin = a->Cin;
+  p.KC = a->Cin % 64 == 0 ? 64 : (a->Cin % 32 == 0 ? 32 : 16);
+  p.n_kc = a->Cin / p.KC;
+  p.n_taps = a->n_taps;
+  for (int i = 0; i < a->n_taps; ++i) {
+    p.dt[i] = a->tap_dt[i]; p.dh[i] = a->tap_dh[i]; p.dw[i] = a->tap_dw[i];
+  }
+  // ---- N tile
+  p.Cout = a->Cout;
+  {
+    const int g = a->n_group > 0 ? a->n_group : a->w_rows;
+    int bn = 0;
+    for (int c = 256; c >= 16; c -= 16)
+      if (g % c == 0) { bn = c; break; }
+    if (a->n_group == 0 && bn < 64 && a->w_rows > 256) bn = 256;  // awkward Cout: partial last tile
+    p.BN = bn;
+    p.n_nt = (a->w_rows + bn - 1) / bn;
+  }
+  p.a_bytes = 128 * p.KC * 2;
+  p.stage_bytes = (p.a_bytes + p.BN * p.KC * 2 + 1023) / 1024 * 1024;
+  p.stages = (kConvSmemBudget - 2048) / p.stage_bytes;
+  if (p.stages > kConvMaxStages) p.stages = kConvMaxStages;
+  OVB_CHECK_ARG(p.stages >= 2, "ovb_conv3d: tile does not fit shared memory (BN=%d KC=%d)", p.BN, p.KC);
+  p.bias = a->bias;
+  p.out = a->out;
+  p.resid = reinterpret_cast<const __nv_bfloat16*>(a->resid);
+  p.os_t = a->os_t; p.os_h = a->os_h; p.os_w = a->os_w; p.out_base = a->out_base;
+  p.n_group = a->n_group > 0 ? a->n_group : 0;
+  p.group_stride = a->group_stride;
+  if (p.n_group == 0) p.n_group = 1 << 30;  // n / n_group == 0 for every n
+  p.out_mode = a->out_mode;
+  p.plane_stride = a->plane_stride;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(a->Cin), static_cast<uint64_t>(a->Wi),
+                              static_cast<uint64_t>(a->Hi), static_cast<uint64_t>(a->Ti)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(a->Cin) * 2,
+                                 static_cast<uint64_t>(a->Cin) * 2 * a->Wi,
+                                 static_cast<uint64_t>(a->Cin) * 2 * a->Wi * a->Hi};
+    // with an element stride s the box spans s*n source elements and delivers n of them
+    const uint32_t box[4] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(bw * a->sw),
+                             static_cast<uint32_t>(p.bh * a->sh), 1};
+    const uint32_t estr[4] = {1, static_cast<uint32_t>(a->sw), static_cast<uint32_t>(a->sh), 1};
+    OVB_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "ovb_conv3d: strided box too large");
+    int rc = encode_tmap_bf16_ex(&tmA, a->x, 4, dims, strides, box, estr, p.KC * 2);
+    if (rc != OVB_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->n_taps) * a->Cin, static_cast<uint64_t>(a->w_rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(a->n_taps) * a->Cin * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.BN)};
+    int rc = encode_tmap_bf16_ex(&tmB, a->w, 2, dims, strides, box, nullptr, p.KC * 2);
+    if (rc != OVB_OK) return rc;
+  }
+
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kConvSmemBudget + 2048));
+    attr_set = true;
+  }
+  const long long num_tiles = static_cast<long long>(p.To) * p.n_ht * p.n_wt * p.n_nt;
+  OVB_CHECK_ARG(num_tiles < (1ll << 31), "ovb_conv3d: too many tiles");
+  const int sms = device_sm_count();
+  const int grid = num_tiles < sms ? static_cast<int>(num_tiles) : sms;
+  conv3d_igemm_kernel<<<grid, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}

@@ -37,7 +37,7 @@ struct GemmParams {
   void* out;
   long long ldo;
   int epilogue;
-  const float* resid;
+  const void* resid;
   long long ldr;
   const float* gate;
   long long gate_row_stride, gate_sample_stride;
@@ -192,10 +192,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[2 * j + 1] += f.y;
               }
             }
-            if (p.epilogue == OVB_EPI_BF16 || p.epilogue == OVB_EPI_GELU_BF16) {
+            if (p.epilogue == OVB_EPI_BF16 || p.epilogue == OVB_EPI_GELU_BF16 ||
+                p.epilogue == OVB_EPI_RESID_BF16) {
               if (p.epilogue == OVB_EPI_GELU_BF16) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
+              } else if (p.epilogue == OVB_EPI_RESID_BF16) {
+                const uint4 rw = *reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.resid) + static_cast<long long>(row) * p.ldr + col);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(r2[j]);
+                  v[2 * j] = bf16_round(v[2 * j]) + f.x;
+                  v[2 * j + 1] = bf16_round(v[2 * j + 1]) + f.y;
+                }
               }
               uint4 o;
               o.x = pack_bf16x2(v[0], v[1]);
@@ -206,7 +217,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else {
               float* optr = reinterpret_cast<float*>(p.out) + obase + g * 8;
               if (p.epilogue != OVB_EPI_F32) {
-                const float* rptr = p.resid + static_cast<long long>(row) * p.ldr + col;
+                const float* rptr = reinterpret_cast<const float*>(p.resid) + static_cast<long long>(row) * p.ldr + col;
                 const float4 x0 = *reinterpret_cast<const float4*>(rptr);
                 const float4 x1 = *reinterpret_cast<const float4*>(rptr + 4);
                 float gt[8];
@@ -258,12 +269,16 @@ extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
   OVB_CHECK_ARG(a->N % 8 == 0 && a->K % 8 == 0, "ovb_gemm_bf16: N and K must be multiples of 8");
   OVB_CHECK_ARG(a->lda % 8 == 0 && a->ldw % 8 == 0 && a->ldo % 8 == 0,
                 "ovb_gemm_bf16: leading dims must be multiples of 8 elements");
-  OVB_CHECK_ARG(a->epilogue >= OVB_EPI_BF16 && a->epilogue <= OVB_EPI_F32,
+  OVB_CHECK_ARG(a->epilogue >= OVB_EPI_BF16 && a->epilogue <= OVB_EPI_RESID_BF16,
                 "ovb_gemm_bf16: unknown epilogue %d", a->epilogue);
   const bool needs_resid =
       a->epilogue == OVB_EPI_RESID_F32 || a->epilogue == OVB_EPI_GATE_RESID_F32;
   OVB_CHECK_ARG(!needs_resid || (a->resid != nullptr && a->ldr % 4 == 0),
                 "ovb_gemm_bf16: residual epilogue needs resid with ldr %% 4 == 0");
+  OVB_CHECK_ARG(a->epilogue != OVB_EPI_RESID_BF16 ||
+                    (a->resid != nullptr && a->ldr % 8 == 0 && a->n_split <= 1 &&
+                     reinterpret_cast<uintptr_t>(a->resid) % 16 == 0),
+                "ovb_gemm_bf16: bf16 residual epilogue needs a 16-byte aligned resid, ldr %% 8 == 0, no n_split");
   OVB_CHECK_ARG(a->epilogue != OVB_EPI_GATE_RESID_F32 ||
                     (a->gate != nullptr && a->rows_per_sample > 0 && a->gate_row_stride % 4 == 0 &&
                      a->gate_sample_stride % 4 == 0),
@@ -304,7 +319,7 @@ extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
   p.out = a->out;
   p.ldo = a->ldo;
   p.epilogue = a->epilogue;
-  p.resid = reinterpret_cast<const float*>(a->resid);
+  p.resid = a->resid;
   p.ldr = a->ldr;
   p.gate = reinterpret_cast<const float*>(a->gate);
   p.gate_row_stride = a->gate_row_stride;

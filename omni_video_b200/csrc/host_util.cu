@@ -38,6 +38,12 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap_bf16_ex(out, gptr, rank, dims, strides_bytes, box, nullptr, 128);
+}
+
+int encode_tmap_bf16_ex(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box,
+                        const uint32_t* elem_strides, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled not available from the CUDA driver");
@@ -50,7 +56,14 @@ int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_
   for (int i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides != nullptr ? elem_strides[i] : 1;
+  }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
+  if (static_cast<int>(box[0]) * 2 > swizzle_bytes) {
+    set_last_error("TMA inner box of %u bf16 exceeds the %d-byte swizzle span", box[0], swizzle_bytes);
+    return OVB_ERR_INVALID_ARGUMENT;
   }
   for (int i = 0; i + 1 < rank; ++i) {
     gstrides[i] = strides_bytes[i];
@@ -62,7 +75,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                   const_cast<void*>(gptr), gdims, gstrides, gbox, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",

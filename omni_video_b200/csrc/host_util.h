@@ -36,6 +36,11 @@ void set_last_error(const char* fmt, ...);
 int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
 
+// General form: element strides per dim (1 = dense) and swizzle span in bytes (128, 64 or 32).
+int encode_tmap_bf16_ex(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box,
+                        const uint32_t* elem_strides, int swizzle_bytes);
+
 int device_sm_count();
 void count_launch();
 

@@ -1,0 +1,226 @@
+// HBM-bound kernels of the Wan2.1 VAE path: channel RMS_norm (+SiLU) on channels-last voxels,
+// planar <-> channels-last converters with the latent (de)normalisation folded in, and the row
+// softmax of the single-head d=384 attention.  16-byte vector accesses throughout.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace ovb {
+
+__device__ __forceinline__ void unpack8(const uint4& w, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMS_norm over C (+SiLU).  Bytes/element: 2 (bf16 in) + 2 (bf16 out) = 4.
+// A group of LPV lanes (16 or 32) owns one voxel: lane l handles the 16-byte chunks l, l+LPV, ...
+// of the voxel's C*2 contiguous bytes (C/8 chunks: 12 / 24 / 48 for C = 96 / 192 / 384), so a warp
+// reads 2 (or 1) whole voxels = one contiguous span, and the sum of squares is a shuffle reduction
+// inside the group.  MAXC chunks per lane are kept in registers so x is read exactly once.
+template <int LPV, int MAXC>
+__global__ void __launch_bounds__(256) rmsnorm_silu_cl_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ gamma,
+                                                               __nv_bfloat16* __restrict__ out,
+                                                               long long n_vox, int C, int silu) {
+  const int lane = threadIdx.x & (LPV - 1);
+  constexpr int kGroupsPerWarp = 32 / LPV;
+  const int sub = (threadIdx.x & 31) / LPV;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int chunks_all = C >> 3;
+  const float sqrt_c = sqrtf(static_cast<float>(C));
+  // warp-uniform trip count: the shuffles below need all 32 lanes
+  for (long long v0 = warp_id * kGroupsPerWarp; v0 < n_vox; v0 += n_warps * kGroupsPerWarp) {
+    const long long v = v0 + sub;
+    const int chunks = v < n_vox ? chunks_all : 0;
+    const uint4* src = reinterpret_cast<const uint4*>(x + v * C);
+    uint4 raw[MAXC];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + i * LPV;
+      if (c < chunks) {
+        raw[i] = src[c];
+        float f[8];
+        unpack8(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+      }
+    }
+#pragma unroll
+    for (int o = LPV / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+    uint4* dst = reinterpret_cast<uint4*>(out + v * C);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + i * LPV;
+      if (c < chunks) {
+        float f[8];
+        unpack8(raw[i], f);
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + c * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = f[j] * inv * g[j];
+          if (silu) y = y / (1.0f + __expf(-y));
+          f[j] = y;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        dst[c] = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// planar fp32 [C][n] -> channels-last bf16 [n][Cpad] (affine per channel, zero padded channels).
+// One thread per voxel; reads are coalesced along n per channel plane, writes are Cpad*2 bytes
+// contiguous per thread.  Only used on the small boundary tensors (latent z, input video).
+__global__ void planar_to_cl_kernel(const float* __restrict__ src, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                                    int C, int Cpad, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c0 = 0; c0 < Cpad; c0 += 8) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      f[j] = c < C ? src[c * n + i] * scale[c] + shift[c] : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + i * Cpad + c0) = o;
+  }
+}
+
+__global__ void cl_to_planar_kernel(const __nv_bfloat16* __restrict__ src, int Cs,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    float* __restrict__ out, int C, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < C; ++c)
+    out[c * n + i] = __bfloat162float(src[i * Cs + c]) * scale[c] + shift[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax: fp32 scores -> bf16 probabilities.  One CTA per row, three passes over a row that
+// stays in L1/L2 (rows are <= 14400 floats = 56 KB).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long lds,
+                                                            __nv_bfloat16* __restrict__ P, long long ldp,
+                                                            int cols, float scale_log2) {
+  __shared__ float red[32];
+  const float* s = S + blockIdx.x * lds;
+  __nv_bfloat16* p = P + blockIdx.x * ldp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, s[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += exp2f((s[c] - m) * scale_log2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    p[c] = __float2bfloat16_rn(exp2f((s[c] - m) * scale_log2) * inv);
+}
+
+}  // namespace ovb
+
+extern "C" int ovb_rmsnorm_silu_cl(const void* x, const float* gamma, void* out, int64_t n_vox,
+                                   int32_t C, int32_t silu, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(x && gamma && out, "ovb_rmsnorm_silu_cl: null pointer");
+  OVB_CHECK_ARG(n_vox > 0 && C > 0 && C % 8 == 0 && C <= 1024,
+                "ovb_rmsnorm_silu_cl: bad shape n_vox=%lld C=%d (C %% 8 == 0, C <= 1024)",
+                static_cast<long long>(n_vox), C);
+  OVB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                 reinterpret_cast<uintptr_t>(gamma)) % 16 == 0,
+                "ovb_rmsnorm_silu_cl: pointers must be 16-byte aligned");
+  const int chunks = C / 8;
+  const int threads = 256;
+  const int sms = device_sm_count();
+  auto s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
+  if (chunks <= 16) {
+    const long long groups_needed = n_vox;
+    long long blocks = (groups_needed * 16 + threads - 1) / threads;
+    if (blocks > sms * 16) blocks = sms * 16;
+    rmsnorm_silu_cl_kernel<16, 1><<<static_cast<int>(blocks), threads, 0, s>>>(xi, gamma, xo, n_vox, C, silu);
+  } else {
+    long long blocks = (n_vox * 32 + threads - 1) / threads;
+    if (blocks > sms * 16) blocks = sms * 16;
+    if (chunks <= 32)
+      rmsnorm_silu_cl_kernel<32, 1><<<static_cast<int>(blocks), threads, 0, s>>>(xi, gamma, xo, n_vox, C, silu);
+    else if (chunks <= 64)
+      rmsnorm_silu_cl_kernel<32, 2><<<static_cast<int>(blocks), threads, 0, s>>>(xi, gamma, xo, n_vox, C, silu);
+    else
+      rmsnorm_silu_cl_kernel<32, 4><<<static_cast<int>(blocks), threads, 0, s>>>(xi, gamma, xo, n_vox, C, silu);
+  }
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_planar_to_cl(const float* src, const float* scale, const float* shift, void* out,
+                                int32_t C, int32_t Cpad, int64_t n, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(src && scale && shift && out, "ovb_planar_to_cl: null pointer");
+  OVB_CHECK_ARG(C > 0 && Cpad >= C && Cpad % 8 == 0 && n > 0, "ovb_planar_to_cl: bad shape C=%d Cpad=%d", C, Cpad);
+  const int threads = 256;
+  const long long blocks = (n + threads - 1) / threads;
+  planar_to_cl_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, scale, shift, reinterpret_cast<__nv_bfloat16*>(out), C, Cpad, n);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_cl_to_planar(const void* src, int32_t Cs, const float* scale, const float* shift,
+                                float* out, int32_t C, int64_t n, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(src && scale && shift && out, "ovb_cl_to_planar: null pointer");
+  OVB_CHECK_ARG(C > 0 && Cs >= C && n > 0, "ovb_cl_to_planar: bad shape C=%d Cs=%d", C, Cs);
+  const int threads = 256;
+  const long long blocks = (n + threads - 1) / threads;
+  cl_to_planar_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), Cs, scale, shift, out, C, n);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int32_t rows,
+                                int32_t cols, float scale, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(S && P && rows > 0 && cols > 0 && lds >= cols && ldp >= cols, "ovb_softmax_rows: bad arguments");
+  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, cols, scale * 1.4426950408889634f);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}

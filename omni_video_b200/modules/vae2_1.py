@@ -1,0 +1,435 @@
+"""B200-native Wan2.1 causal-3D VAE (drop-in for reference omnivideo/modules/vae2_1.py).
+
+`Wan2_1_VAE(z_dim, vae_pth, dtype, device)` with `.encode(videos)` / `.decode(zs)` and the
+attributes the pipeline touches (`.model`, `.mean`, `.std`, `.scale`, `.model.z_dim`;
+x2x_gen_unified.py:328,506-510) keeps the reference's surface; the module tree below carries the
+reference's parameter names so `Wan2.1_VAE.pth` loads unchanged.  None of the leaf `forward`s runs
+on the hot path: `VAEEngine` walks the parameters and drives libovb200:
+
+    reference op (vae2_1.py)                               kernel
+    -----------------------------------------------------  ---------------------------------------
+    CausalConv3d 3x3x3 / 1x1x1 / (3,1,1) (:16-35)           ovb_conv3d  (implicit GEMM, tcgen05 + TMA)
+    RMS_norm + SiLU (:38-53, :194-196)                      ovb_rmsnorm_silu_cl
+    Upsample(nearest 2x) + Conv2d 3x3 (:75-84)              ovb_conv3d x4 (one 2x2 conv per output phase)
+    upsample3d time_conv + frame interleave (:100-136)      ovb_conv3d (channel-group -> frame epilogue)
+    ZeroPad2d(0,1,0,1) + Conv2d s2 (:86-95)                 ovb_conv3d (element-strided TMA boxes)
+    downsample3d time_conv stride 2 (:142-158)              ovb_conv3d (st = 2)
+    AttentionBlock, one head, d = C (:222-261)              ovb_gemm_bf16 + ovb_softmax_rows
+    latent (de)normalisation, clamp (:535-550, :660)        ovb_planar_to_cl / ovb_cl_to_planar / conv epilogue
+
+All frames of a clip are processed in ONE pass over channels-last bf16 tensors; the reference's
+temporal chunk loop with `feat_cache` (:515-567) is exactly causal zero padding plus the first-frame
+rules of upsample3d / downsample3d (pinned by tests/test_oracle_vae_golden.py).
+The reference computes the VAE in fp32; bf16 tensor-core math here is held to PSNR >= 40 dB.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import re
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops, vae_ops
+from ..ops import EPI_BF16, EPI_F32, EPI_RESID_BF16
+from ..vae_ops import CONV_OUT_BF16, CONV_OUT_F32_PLANAR_CLAMP
+
+__all__ = ["Wan2_1_VAE", "WanVAE_", "VAEEngine"]
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+# reference vae2_1.py:628-635
+_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508,
+         0.4134, -0.0715, 0.5517, -0.3632, -0.1922, -0.9497, 0.2503, -0.2921]
+_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
+        3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.9160]
+
+
+# ------------------------------------------------------------------------------------------------
+# Parameter containers with the reference's names (vae2_1.py:16-471)
+# ------------------------------------------------------------------------------------------------
+class CausalConv3d(nn.Conv3d):
+    """reference :16-35 — parameters only; the arithmetic is VAEEngine's."""
+
+    def forward(self, x, cache_x=None):  # pragma: no cover
+        raise NotImplementedError("use Wan2_1_VAE.encode/decode (VAEEngine); leaf modules only hold parameters")
+
+
+class RMS_norm(nn.Module):
+    """reference :38-53"""
+
+    def __init__(self, dim, channel_first=True, images=True, bias=False):
+        super().__init__()
+        shape = (dim, 1, 1) if images else (dim, 1, 1, 1)
+        self.gamma = nn.Parameter(torch.ones(shape if channel_first else (dim,)))
+        self.scale = dim ** 0.5
+
+
+class Resample(nn.Module):
+    """reference :65-182"""
+
+    def __init__(self, dim, mode):
+        assert mode in ("upsample2d", "upsample3d", "downsample2d", "downsample3d")
+        super().__init__()
+        self.dim, self.mode = dim, mode
+        if mode.startswith("upsample"):
+            self.resample = nn.Sequential(nn.Identity(), nn.Conv2d(dim, dim // 2, 3, padding=1))
+            if mode == "upsample3d":
+                self.time_conv = CausalConv3d(dim, dim * 2, (3, 1, 1), padding=(1, 0, 0))
+        else:
+            self.resample = nn.Sequential(nn.Identity(), nn.Conv2d(dim, dim, 3, stride=(2, 2)))
+            if mode == "downsample3d":
+                self.time_conv = CausalConv3d(dim, dim, (3, 1, 1), stride=(2, 1, 1), padding=(0, 0, 0))
+
+
+class ResidualBlock(nn.Module):
+    """reference :185-219"""
+
+    def __init__(self, in_dim, out_dim, dropout=0.0):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.residual = nn.Sequential(
+            RMS_norm(in_dim, images=False), nn.SiLU(), CausalConv3d(in_dim, out_dim, 3, padding=1),
+            RMS_norm(out_dim, images=False), nn.SiLU(), nn.Dropout(dropout),
+            CausalConv3d(out_dim, out_dim, 3, padding=1))
+        self.shortcut = CausalConv3d(in_dim, out_dim, 1) if in_dim != out_dim else nn.Identity()
+
+
+class AttentionBlock(nn.Module):
+    """reference :222-261"""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.norm = RMS_norm(dim)
+        self.to_qkv = nn.Conv2d(dim, dim * 3, 1)
+        self.proj = nn.Conv2d(dim, dim, 1)
+        nn.init.zeros_(self.proj.weight)
+
+
+class Encoder3d(nn.Module):
+    """reference :264-365"""
+
+    def __init__(self, dim=128, z_dim=4, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                 temperal_downsample=(True, True, False), dropout=0.0):
+        super().__init__()
+        dims = [dim * u for u in [1] + list(dim_mult)]
+        scale = 1.0
+        self.conv1 = CausalConv3d(3, dims[0], 3, padding=1)
+        downs = []
+        for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(num_res_blocks):
+                downs.append(ResidualBlock(in_dim, out_dim, dropout))
+                if scale in attn_scales:
+                    downs.append(AttentionBlock(out_dim))
+                in_dim = out_dim
+            if i != len(dim_mult) - 1:
+                downs.append(Resample(out_dim, "downsample3d" if temperal_downsample[i] else "downsample2d"))
+                scale /= 2.0
+        self.downsamples = nn.Sequential(*downs)
+        self.middle = nn.Sequential(ResidualBlock(out_dim, out_dim, dropout), AttentionBlock(out_dim),
+                                    ResidualBlock(out_dim, out_dim, dropout))
+        self.head = nn.Sequential(RMS_norm(out_dim, images=False), nn.SiLU(),
+                                  CausalConv3d(out_dim, z_dim, 3, padding=1))
+
+
+class Decoder3d(nn.Module):
+    """reference :368-471"""
+
+    def __init__(self, dim=128, z_dim=4, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                 temperal_upsample=(False, True, True), dropout=0.0):
+        super().__init__()
+        dims = [dim * u for u in [dim_mult[-1]] + list(dim_mult[::-1])]
+        scale = 1.0 / 2 ** (len(dim_mult) - 2)
+        self.conv1 = CausalConv3d(z_dim, dims[0], 3, padding=1)
+        self.middle = nn.Sequential(ResidualBlock(dims[0], dims[0], dropout), AttentionBlock(dims[0]),
+                                    ResidualBlock(dims[0], dims[0], dropout))
+        ups = []
+        for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+            if i in (1, 2, 3):
+                in_dim = in_dim // 2
+            for _ in range(num_res_blocks + 1):
+                ups.append(ResidualBlock(in_dim, out_dim, dropout))
+                if scale in attn_scales:
+                    ups.append(AttentionBlock(out_dim))
+                in_dim = out_dim
+            if i != len(dim_mult) - 1:
+                ups.append(Resample(out_dim, "upsample3d" if temperal_upsample[i] else "upsample2d"))
+                scale *= 2.0
+        self.upsamples = nn.Sequential(*ups)
+        self.head = nn.Sequential(RMS_norm(out_dim, images=False), nn.SiLU(),
+                                  CausalConv3d(out_dim, 3, 3, padding=1))
+
+
+class WanVAE_(nn.Module):
+    """reference :482-589 (constructor and encode/decode signatures)."""
+
+    def __init__(self, dim=128, z_dim=4, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                 temperal_downsample=(True, True, False), dropout=0.0):
+        super().__init__()
+        self.dim, self.z_dim = dim, z_dim
+        self.dim_mult, self.num_res_blocks = list(dim_mult), num_res_blocks
+        self.attn_scales = list(attn_scales)
+        self.temperal_downsample = list(temperal_downsample)
+        self.temperal_upsample = list(temperal_downsample)[::-1]
+        self.encoder = Encoder3d(dim, z_dim * 2, dim_mult, num_res_blocks, attn_scales,
+                                 self.temperal_downsample, dropout)
+        self.conv1 = CausalConv3d(z_dim * 2, z_dim * 2, 1)
+        self.conv2 = CausalConv3d(z_dim, z_dim, 1)
+        self.decoder = Decoder3d(dim, z_dim, dim_mult, num_res_blocks, attn_scales,
+                                 self.temperal_upsample, dropout)
+        self._engine = None
+
+    def engine(self, scale) -> "VAEEngine":
+        mean, inv_std = scale
+        if self._engine is None:
+            self._engine = VAEEngine(self, torch.as_tensor(mean), 1.0 / torch.as_tensor(inv_std))
+        return self._engine
+
+    def encode(self, x, scale):
+        """x: [1, 3, T, H, W] -> normalised mu [1, z, T', h, w] (reference :515-541)."""
+        assert x.shape[0] == 1
+        return self.engine(scale).encode([x[0]])[0].unsqueeze(0)
+
+    def decode(self, z, scale):
+        """z: [1, z, T, h, w] -> [1, 3, 1+4(T-1), 8h, 8w], NOT clamped (reference :543-567)."""
+        assert z.shape[0] == 1
+        return self.engine(scale).decode([z[0]], clamp=False)[0].unsqueeze(0)
+
+    def clear_cache(self):  # the single-pass engine keeps no temporal cache (reference :581-589)
+        pass
+
+
+def _video_vae(pretrained_path=None, z_dim=None, device="cpu", **kwargs):
+    """reference :591-615"""
+    cfg = dict(dim=96, z_dim=z_dim, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+               temperal_downsample=[False, True, True], dropout=0.0)
+    cfg.update(**kwargs)
+    if pretrained_path is None:
+        return WanVAE_(**cfg)
+    with torch.device("meta"):
+        model = WanVAE_(**cfg)
+    logging.info(f"loading {pretrained_path}")
+    model.load_state_dict(torch.load(pretrained_path, map_location=device), assign=True)
+    return model
+
+
+class Wan2_1_VAE:
+    """reference :618-662.  `vae_pth=None` builds a randomly initialised model (tests / benchmarks
+    without checkpoints)."""
+
+    def __init__(self, z_dim=16, vae_pth="cache/vae_step_411000.pth", dtype=torch.float, device="cuda"):
+        self.dtype, self.device = dtype, device
+        self.mean = torch.tensor(_MEAN, dtype=dtype, device=device)
+        self.std = torch.tensor(_STD, dtype=dtype, device=device)
+        self.scale = [self.mean, 1.0 / self.std]
+        self.model = _video_vae(pretrained_path=vae_pth, z_dim=z_dim).eval().requires_grad_(False).to(device)
+
+    def _engine(self) -> "VAEEngine":
+        return self.model.engine(self.scale)
+
+    def encode(self, videos):
+        """videos: list of [3, T, H, W] -> list of fp32 [16, T', H/8, W/8]."""
+        return self._engine().encode(videos)
+
+    def decode(self, zs):
+        """zs: list of [16, T, h, w] -> list of fp32 [3, 1+4(T-1), 8h, 8w] clamped to [-1, 1]."""
+        return self._engine().decode(zs, clamp=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# Engine
+# ------------------------------------------------------------------------------------------------
+class VAEEngine:
+    """Runs encode/decode of a `WanVAE_`-shaped module (ours or the reference's) on libovb200."""
+
+    def __init__(self, model: nn.Module, mean: torch.Tensor, std: torch.Tensor):
+        self.m = model
+        self.mean_host, self.std_host = mean.detach().float().cpu(), std.detach().float().cpu()
+        self._packed: Dict[str, object] = {}
+        self._key = None
+
+    # -------------------------------------------------------------------------------- weights
+    def _params(self) -> Dict[str, torch.Tensor]:
+        key = tuple((p.device, p._version, p.data_ptr()) for p in self.m.parameters())
+        if key != self._key:
+            self._packed, self._key = {}, key
+            self._sd = {k: v for k, v in self.m.state_dict().items()}
+            dev = next(self.m.parameters()).device
+            if dev.type != "cuda":
+                raise ops._lib.OvbError("VAE parameters must live on a CUDA device: the B200 path has "
+                                        "no CPU fallback")
+            self.dev = dev
+            z = self.mean_host.numel()
+            self.mean, self.std = self.mean_host.to(dev), self.std_host.to(dev)
+            self._ones = {n: torch.ones(n, device=dev, dtype=f32) for n in (3, z, 2 * z)}
+            self._zeros = {n: torch.zeros(n, device=dev, dtype=f32) for n in (3, z, 2 * z)}
+        return self._sd
+
+    def _conv(self, name: str, **kw) -> vae_ops.PackedConv:
+        if name not in self._packed:
+            sd = self._params()
+            self._packed[name] = vae_ops.pack_conv3d(sd[name + ".weight"], sd[name + ".bias"], **kw)
+        return self._packed[name]
+
+    def _gamma(self, name: str) -> torch.Tensor:
+        if name not in self._packed:
+            self._packed[name] = self._params()[name].detach().float().reshape(-1).contiguous()
+        return self._packed[name]
+
+    def _mat(self, name: str, rows: Optional[slice] = None) -> torch.Tensor:
+        key = (name, None if rows is None else (rows.start, rows.stop))
+        if key not in self._packed:
+            w = self._params()[name].detach()
+            w = w.reshape(w.shape[0], -1)
+            if rows is not None:
+                w = w[rows]
+            self._packed[key] = w.to(bf16).contiguous()
+        return self._packed[key]
+
+    # -------------------------------------------------------------------------------- blocks
+    def _causal_conv(self, x, name, resid=None):
+        T, H, W, _ = x.shape
+        return vae_ops.conv3d(x, self._conv(name), (T, H, W), resid=resid)
+
+    def _residual_block(self, x, p):
+        sd = self._params()
+        h = self._causal_conv(x, p + "shortcut") if (p + "shortcut.weight") in sd else x
+        a = vae_ops.rmsnorm_silu(x, self._gamma(p + "residual.0.gamma"))
+        b = self._causal_conv(a, p + "residual.2")
+        del a
+        vae_ops.rmsnorm_silu(b, self._gamma(p + "residual.3.gamma"), out=b)     # in place: elementwise
+        return self._causal_conv(b, p + "residual.6", resid=h)
+
+    def _attention_block(self, x, p):
+        T, H, W, Cc = x.shape
+        hw = H * W
+        if hw % 8 != 0:
+            raise NotImplementedError(f"VAE attention needs h*w % 8 == 0 (got {H}x{W})")
+        x2 = x.view(T * hw, Cc)
+        xn = vae_ops.rmsnorm_silu(x2, self._gamma(p + "norm.gamma"), silu=False)
+        sd = self._params()
+        bias = sd[p + "to_qkv.bias"].detach().to(bf16)
+        wqk = self._mat(p + "to_qkv.weight", slice(0, 2 * Cc))
+        wv = self._mat(p + "to_qkv.weight", slice(2 * Cc, 3 * Cc))
+        qk = ops.gemm(xn, wqk, bias[:2 * Cc].contiguous(), epilogue=EPI_BF16)   # [T*hw, 2C]
+        o = torch.empty((T * hw, Cc), device=x.device, dtype=bf16)
+        S = torch.empty((hw, hw), device=x.device, dtype=f32)
+        P = torch.empty((hw, hw), device=x.device, dtype=bf16)
+        vt = torch.empty((Cc, hw), device=x.device, dtype=bf16)
+        bv = bias[2 * Cc:].contiguous()
+        scale = 1.0 / math.sqrt(Cc)
+        for f in range(T):
+            rows = slice(f * hw, (f + 1) * hw)
+            ops.gemm(wv, xn[rows], None, epilogue=EPI_BF16, out=vt)              # V^T = Wv Xn^T   [C, hw]
+            ops.gemm(qk[rows, :Cc], qk[rows, Cc:], None, epilogue=EPI_F32, out=S)  # Q K^T        [hw, hw]
+            vae_ops.softmax_rows(S, scale, out=P)
+            ops.gemm(P, vt, bv, epilogue=EPI_BF16, out=o[rows])                   # P V + b_v (rows of P sum to 1)
+        wp = self._mat(p + "proj.weight")
+        bp = sd[p + "proj.bias"].detach().to(bf16).contiguous()
+        y = ops.gemm(o, wp, bp, epilogue=EPI_RESID_BF16, resid=x2)
+        return y.view(T, H, W, Cc)
+
+    def _upsample(self, x, p, three_d: bool):
+        T, H, W, Cc = x.shape
+        sd = self._params()
+        if three_d and T > 1:
+            # time_conv over frames 1.. (zero left context), channel halves -> consecutive frames
+            pc = self._conv(p + "time_conv")
+            y = torch.empty((1 + 2 * (T - 1), H, W, Cc), device=x.device, dtype=bf16)
+            y[0].copy_(x[0])
+            fr = H * W * Cc
+            vae_ops.conv3d(x[1:], pc, (T - 1, H, W), out=y, out_strides=(2 * fr, W * Cc, Cc), out_base=fr,
+                           n_group=Cc, group_stride=fr)
+            x, T = y, y.shape[0]
+        key = p + "resample.1#phases"
+        if key not in self._packed:
+            self._packed[key] = vae_ops.pack_upsample_conv2d(sd[p + "resample.1.weight"],
+                                                             sd[p + "resample.1.bias"])
+        phases = self._packed[key]
+        Co = Cc // 2
+        out = torch.empty((T, 2 * H, 2 * W, Co), device=x.device, dtype=bf16)
+        for (a, b), pc in phases.items():
+            vae_ops.conv3d(x, pc, (T, H, W), out=out, out_strides=(4 * H * W * Co, 4 * W * Co, 2 * Co),
+                           out_base=(a * 2 * W + b) * Co)
+        return out
+
+    def _downsample(self, x, p, three_d: bool):
+        T, H, W, Cc = x.shape
+        Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1                     # ZeroPad2d(0,1,0,1) + k3 s2
+        pc = self._conv(p + "resample.1", stride=(1, 2, 2), spatial_pad=(0, 0))
+        x = vae_ops.conv3d(x, pc, (T, Ho, Wo))
+        if three_d and T > 1:
+            # out[0] = x[0]; out[j] = time_conv(x[2j-2], x[2j-1], x[2j])  (stride 2, no padding)
+            To = 1 + (T - 1) // 2
+            pt = self._conv(p + "time_conv", causal_pad=0, stride=(2, 1, 1))
+            y = torch.empty((To, Ho, Wo, Cc), device=x.device, dtype=bf16)
+            y[0].copy_(x[0])
+            fr = Ho * Wo * Cc
+            vae_ops.conv3d(x, pt, (To - 1, Ho, Wo), out=y, out_strides=(fr, Wo * Cc, Cc), out_base=fr)
+            x = y
+        return x
+
+    def _stack(self, x, prefix, up: bool):
+        sd = self._params()
+        pat = re.compile(re.escape(prefix) + r"(\d+)\.")
+        idx = sorted({int(mm.group(1)) for k in sd for mm in [pat.match(k)] if mm})
+        for i in idx:
+            p = f"{prefix}{i}."
+            if (p + "residual.2.weight") in sd:
+                x = self._residual_block(x, p)
+            elif (p + "to_qkv.weight") in sd:
+                x = self._attention_block(x, p)
+            elif (p + "resample.1.weight") in sd:
+                three_d = (p + "time_conv.weight") in sd
+                x = self._upsample(x, p, three_d) if up else self._downsample(x, p, three_d)
+            else:  # pragma: no cover
+                raise KeyError(f"unknown VAE module at {p}")
+        return x
+
+    # -------------------------------------------------------------------------------- entry points
+    @torch.no_grad()
+    def decode(self, zs: List[torch.Tensor], clamp: bool = True) -> List[torch.Tensor]:
+        self._params()
+        outs = []
+        for z in zs:
+            z = z.to(self.dev, dtype=f32).contiguous()
+            zc = z.shape[0]
+            x = vae_ops.planar_to_cl(z, self.std, self.mean, 16)                 # z*std + mean (:546-550)
+            assert zc == 16, "Wan2.1 VAE has z_dim 16"
+            T, H, W, _ = x.shape
+            x = vae_ops.conv3d(x, self._conv("conv2"), (T, H, W))                # 1x1x1 (:552)
+            x = self._causal_conv(x, "decoder.conv1")
+            x = self._stack(x, "decoder.middle.", up=True)
+            x = self._stack(x, "decoder.upsamples.", up=True)
+            vae_ops.rmsnorm_silu(x, self._gamma("decoder.head.0.gamma"), out=x)
+            T, H, W, _ = x.shape
+            out = torch.empty((3, T, H, W), device=self.dev, dtype=f32)
+            vae_ops.conv3d(x, self._conv("decoder.head.2"), (T, H, W), out=out, out_strides=(H * W, W, 1),
+                           out_mode=CONV_OUT_F32_PLANAR_CLAMP if clamp else vae_ops.CONV_OUT_F32_PLANAR,
+                           plane_stride=T * H * W)
+            outs.append(out)
+        return outs
+
+    @torch.no_grad()
+    def encode(self, videos: List[torch.Tensor]) -> List[torch.Tensor]:
+        self._params()
+        outs = []
+        for v in videos:
+            v = v.to(self.dev, dtype=f32).contiguous()
+            assert v.shape[0] == 3 and (v.shape[1] - 1) % 4 == 0, "video must be [3, 1+4k, H, W]"
+            x = vae_ops.planar_to_cl(v, self._ones[3], self._zeros[3], 16)
+            x = self._causal_conv(x, "encoder.conv1")
+            x = self._stack(x, "encoder.downsamples.", up=False)
+            x = self._stack(x, "encoder.middle.", up=False)
+            vae_ops.rmsnorm_silu(x, self._gamma("encoder.head.0.gamma"), out=x)
+            x = self._causal_conv(x, "encoder.head.2")                            # [T', h, w, 32]
+            T, H, W, _ = x.shape
+            x = vae_ops.conv3d(x, self._conv("conv1"), (T, H, W))                # 1x1x1 (:534)
+            z = self.mean.numel()
+            inv = 1.0 / self.std
+            outs.append(vae_ops.cl_to_planar(x, inv, -self.mean * inv, z))        # (mu - mean)/std (:535-539)
+        return outs

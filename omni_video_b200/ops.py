@@ -10,8 +10,8 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (EPI_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_RESID_F32,  # noqa: F401
-                   LN_AFFINE, LN_MODULATE)
+from ._lib import (EPI_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_RESID_BF16,  # noqa: F401
+                   EPI_RESID_F32, LN_AFFINE, LN_MODULATE)
 
 bf16 = torch.bfloat16
 f32 = torch.float32
@@ -104,6 +104,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, epil
     args.out, args.ldo = out.data_ptr(), ldo
     args.M, args.N, args.K = M, N, K
     args.epilogue = epilogue
+    if epilogue == EPI_RESID_BF16:
+        assert resid is not None and resid.dtype == bf16 and resid.shape == (M, N) and n_split == 1
+        _row_major_2d(resid, "resid")
+        args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
     if epilogue in (EPI_RESID_F32, EPI_GATE_RESID_F32):
         assert resid is not None and resid.dtype == f32 and resid.shape == (M, N)
         _row_major_2d(resid, "resid")
