@@ -102,7 +102,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp < 4) {
     setmaxnreg_dec_72();
-    if (warp == 0 && lane == 0 && n_kv > 0) {
+    if (warp == 0 && n_kv > 0 && elect_one()) {
       // -------------------------------------------------------- TMA producer
       const int col = head * 128;
       mbar_expect_tx(q_full, 2 * kTileBytes);
@@ -123,7 +123,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_3d(sV + s * kTileBytes, &tmV, &v_full[s], col, j * 128, batch);
         tma_load_3d(sV + s * kTileBytes + kBoxBytes, &tmV, &v_full[s], col + 64, j * 128, batch);
       }
-    } else if (warp == 1 && lane == 0 && n_kv > 0) {
+    } else if (warp == 1 && n_kv > 0 && elect_one()) {
       // -------------------------------------------------------- MMA issuer
       const uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // V is MN-major

@@ -97,7 +97,9 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): the compiler then knows exactly one lane runs the loop and
+    // feeds UTMALDG / UTCHMMA from uniform registers without a per-instruction waterfall loop
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = static_cast<uint32_t>(128 * p.KC * 2 + p.BN * p.KC * 2);
@@ -128,7 +130,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
       const uint32_t row_bytes = p.KC * 2;
       const int k_steps = p.KC / 16;

@@ -11,6 +11,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from . import ops as ops_mod
 from ._lib import CONV_OUT_BF16, CONV_OUT_F32_PLANAR, CONV_OUT_F32_PLANAR_CLAMP  # noqa: F401
 from .ops import _need_cuda, _ptr, _stream
 
@@ -123,7 +124,9 @@ def conv3d(x: torch.Tensor, pc: PackedConv, out_extent: Tuple[int, int, int], *,
         assert resid.dtype == bf16 and resid.is_contiguous() and resid.numel() == out.numel()
         a.resid = resid.data_ptr()
     a.out_mode, a.plane_stride = out_mode, plane_stride
+    ev = ops_mod._tl_begin()
     _lib.check(lib.ovb_conv3d(C.byref(a), _stream()), "ovb_conv3d")
+    ops_mod._tl_end(ev, "conv", 2.0 * To * Ho * Wo * pc.cout * pc.n_taps * Cin, (To, Ho, Wo, Cin, pc.cout, pc.n_taps))
     return out
 
 
@@ -138,8 +141,10 @@ def rmsnorm_silu(x: torch.Tensor, gamma: torch.Tensor, silu: bool = True,
     if out is None:
         out = torch.empty_like(x)
     assert out.dtype == bf16 and out.is_contiguous() and out.shape == x.shape
+    ev = ops_mod._tl_begin()
     _lib.check(lib.ovb_rmsnorm_silu_cl(_ptr(x), _ptr(gamma), _ptr(out), x.numel() // Cc, Cc, int(silu),
                                        _stream()), "ovb_rmsnorm_silu_cl")
+    ops_mod._tl_end(ev, "norm", 4.0 * x.numel(), (x.numel() // Cc, Cc))   # "flops" slot = algorithmic bytes
     return out
 
 
