@@ -1,34 +1,42 @@
-// ovb_gemm_bf16: persistent, warp-specialised bf16 GEMM for sm_100a.
+// ovb_gemm_bf16: persistent, warp-specialised bf16 GEMM for sm_100a on CTA PAIRS.
 //
 //   out = epilogue(A[M,K] * W[N,K]^T + bias)
 //
-// One CTA per SM (persistent over 128x256 output tiles, N fastest so that the 148 resident CTAs
-// share a handful of A row-panels and the whole weight matrix stays in the 126 MB L2).
-//   warp 0      TMA producer: 64-wide K slices of A (128 rows) and W (256 rows), 128B-swizzled,
-//               into a 4-stage shared-memory ring (48 KB / stage)
-//   warp 1      single elected thread issues tcgen05.mma (M=128, N=256, K=16) x4 per stage;
-//               tcgen05.commit releases the stage and, on the last K slice, publishes the tile
-//   warp 2      TMEM allocator (all 512 columns = two 128x256 fp32 accumulators, so the epilogue
-//               of tile i overlaps the main loop of tile i+1)
-//   warps 4-7   epilogue: tcgen05.ld 32 columns at a time (one accumulator row per thread),
-//               bias / GELU / gate / fp32-residual math in registers, 16-byte global stores
+// Two CTAs on the two SMs of a TPC form a cluster and compute one 256x256 output tile with
+// tcgen05.mma.cta_group::2 (M = 256): CTA r of the pair owns rows [128r, 128r+128) of the tile (its
+// 128 TMEM lanes) and stages only ITS half of the operands — 128 rows of A and 128 of the 256 rows
+// of W — so each SM reads 8 KB of shared memory per MMA instead of 12 KB.  Measured on B200
+// (scripts/microbench/mma_rate.cu): a 128x256x16 MMA fed from one SM's shared memory takes ~163
+// cycles against the 128-cycle tensor floor because the B operand streams at ~70 B/cycle; halving
+// B per SM removes that bound.
+//   warp 0      TMA producer (each CTA loads its own halves; the transaction bytes of both CTAs
+//               are signalled on the LEADER's full barrier), 6-stage ring, 32 KB / stage / CTA
+//   warp 1      leader CTA only: one elected thread issues the MMAs; tcgen05.commit multicasts the
+//               "stage free" / "accumulator ready" arrivals to both CTAs
+//   warp 2      TMEM allocator (cta_group::2, all 512 columns = two 256-column accumulators, so the
+//               epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 4-7   epilogue: tcgen05.ld 32 columns -> shared-memory transpose (XOR-swizzled 16-byte
+//               chunks, conflict free) -> bias / GELU / gate / residual math on ROW-CONTIGUOUS
+//               16-byte vectors, so every global access of a warp covers whole 64/128-byte row
+//               segments instead of 32 scattered rows.
 //
 // Algorithmic bytes per tile are tiny next to the FLOPs (arithmetic intensity >= 700 FLOP/B for
-// the smallest DiT shape), so the bounding roofline is the tensor pipe; see DESIGN.md §4.
+// the smallest DiT shape), so the bounding roofline is the tensor pipe; see DESIGN.md §3.
 #include "host_util.h"
 #include "ptx.cuh"
 
 namespace ovb {
 
-constexpr int kBM = 128;
-constexpr int kBN = 256;
+constexpr int kBM = 128;          // rows per CTA (256 per pair)
+constexpr int kBN = 256;          // tile width; each CTA stages kBN/2 rows of W
 constexpr int kBK = 64;
-constexpr int kStages = 4;
-constexpr int kABytes = kBM * kBK * 2;  // 16 KB
-constexpr int kBBytes = kBN * kBK * 2;  // 32 KB
+constexpr int kStages = 6;
+constexpr int kABytes = kBM * kBK * 2;        // 16 KB
+constexpr int kBBytes = (kBN / 2) * kBK * 2;  // 16 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 256;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kStagingBytes = 4 * 32 * 32 * 4;  // one 32x32 fp32 transpose buffer per epilogue warp
+constexpr int kGemmSmem = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct GemmParams {
   int M, N, K;
@@ -44,23 +52,28 @@ struct GemmParams {
   int rows_per_sample;
   int n_per_split;  // N / n_split (== N when off)
   long long out_split_stride;
-  int num_m_tiles, num_n_tiles;
+  int num_m_tiles, num_n_tiles;  // 256 x 256 pair tiles
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int kEpi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  float* staging = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;  // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained (leader's copy is used)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + kBK - 1) / kBK;
   const int kb_per_split = (p.k_per_split + kBK - 1) / kBK;
@@ -71,40 +84,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);   // leader's producer: arrive.expect_tx for both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);  // one multicast commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (both CTAs)
     // elect.sync (not `lane == 0`): the compiler then knows exactly one lane runs the loop and
     // feeds UTMALDG / UTCHMMA from uniform registers without a per-instruction waterfall loop
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int n_tile = tile % p.num_n_tiles;
         const int m_tile = tile / p.num_n_tiles;
+        const int row0 = m_tile * 2 * kBM + rank * kBM;
+        const int wrow0 = n_tile * kBN + rank * (kBN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
           const int split = kb / kb_per_split;
           const int kcol = (kb - split * kb_per_split) * kBK;
-          tma_load_3d(sa, &tmA, &full_bar[stage], kcol, m_tile * kBM, split);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBK, n_tile * kBN);
+          tma_load_3d_pair(sa, &tmA, leader_full, kcol, row0, split);
+          tma_load_2d_pair(sb, &tmB, leader_full, kb * kBK, wrow0);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -113,14 +129,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(2 * kBM, kBN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBN;
@@ -133,10 +149,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+            umma_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc], 3);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -149,102 +165,140 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue (both CTAs)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    float* stg = staging + quad * (32 * 32);
+    const uint32_t stg_addr = smem_u32(stg);
+    const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    const int rr_off = lane >> 3;  // row inside a group of 4 in the read phase
+    const int cj = lane & 7;       // 16-byte chunk (4 fp32 columns) in the read phase
+    constexpr bool f32_resid = kEpi == OVB_EPI_RESID_F32 || kEpi == OVB_EPI_GATE_RESID_F32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
-      const int row = m_tile * kBM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = m_tile * 2 * kBM + rank * kBM + quad * 32;
+      // bias of this lane's 4 columns, one chunk ahead: the first fetch is issued before the
+      // accumulator is ready so its latency hides behind the main loop
+      uint2 bw_next = make_uint2(0u, 0u);
+      {
+        const int col = n_tile * kBN + cj * 4;
+        if (p.bias != nullptr && col < p.N) bw_next = *reinterpret_cast<const uint2*>(p.bias + col);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const float* gate_row = nullptr;
-      if (p.epilogue == OVB_EPI_GATE_RESID_F32 && row_ok) {
-        const int sample = row / p.rows_per_sample;
-        const int r_in = row - sample * p.rows_per_sample;
-        gate_row = p.gate + sample * p.gate_sample_stride + r_in * p.gate_row_stride;
-      }
 #pragma unroll 1
       for (int c = 0; c < kBN / 32; ++c) {
         const int col0 = n_tile * kBN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN + c * 32, r);
-        tmem_wait_ld();
-        if (row_ok) {
-          const int seg = col0 / p.n_per_split;
-          const int col_in = col0 - seg * p.n_per_split;
-          const long long obase = seg * p.out_split_stride + static_cast<long long>(row) * p.ldo + col_in;
+        const int col = col0 + cj * 4;
+        const bool col_ok = col < p.N;
+        const uint2 bw = bw_next;
+        if (p.bias != nullptr && col + 32 < p.N && c + 1 < kBN / 32)
+          bw_next = *reinterpret_cast<const uint2*>(p.bias + col + 32);
+        // operands of the residual epilogues: all 8 row groups are requested up front, before
+        // any store of this chunk is issued (a store may alias them as far as the compiler knows)
+        float4 xr[8], gt[8];
+        uint2 xb[8];
+        if constexpr (f32_resid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 8 columns per group
-            const int col = col0 + g * 8;
-            if (col >= p.N) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-            if (p.bias != nullptr) {
-              const uint4 bw = *reinterpret_cast<const uint4*>(p.bias + col);
-              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bw);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(b2[j]);
-                v[2 * j] += f.x;
-                v[2 * j + 1] += f.y;
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + 4 * i + rr_off;
+            xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            gt[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (row < p.M && col_ok) {
+              xr[i] = *reinterpret_cast<const float4*>(
+                  reinterpret_cast<const float*>(p.resid) + static_cast<long long>(row) * p.ldr + col);
+              if constexpr (kEpi == OVB_EPI_GATE_RESID_F32) {
+                const int sample = row / p.rows_per_sample;
+                const int r_in = row - sample * p.rows_per_sample;
+                gt[i] = *reinterpret_cast<const float4*>(p.gate + sample * p.gate_sample_stride +
+                                                         r_in * p.gate_row_stride + col);
               }
             }
-            if (p.epilogue == OVB_EPI_BF16 || p.epilogue == OVB_EPI_GELU_BF16 ||
-                p.epilogue == OVB_EPI_RESID_BF16) {
-              if (p.epilogue == OVB_EPI_GELU_BF16) {
+          }
+        } else if constexpr (kEpi == OVB_EPI_RESID_BF16) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
-              } else if (p.epilogue == OVB_EPI_RESID_BF16) {
-                const uint4 rw = *reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const __nv_bfloat16*>(p.resid) + static_cast<long long>(row) * p.ldr + col);
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rw);
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + 4 * i + rr_off;
+            xb[i] = make_uint2(0u, 0u);
+            if (row < p.M && col_ok)
+              xb[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) +
+                                                      static_cast<long long>(row) * p.ldr + col);
+          }
+        }
+        tmem_wait_ld();
+        // transpose through shared memory: thread = row writes 8 chunks, chunk j at j ^ (row & 7)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = __bfloat1622float2(r2[j]);
-                  v[2 * j] = bf16_round(v[2 * j]) + f.x;
-                  v[2 * j + 1] = bf16_round(v[2 * j + 1]) + f.y;
-                }
-              }
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + g * 8) = o;
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = stg_addr + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(r[4 * j]),
+                       "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        float b4[4];
+        {
+          const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw.x));
+          const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw.y));
+          b4[0] = f0.x; b4[1] = f0.y; b4[2] = f1.x; b4[3] = f1.y;
+        }
+        const int seg = col0 / p.n_per_split;
+        const long long ocol = seg * p.out_split_stride + (col - seg * p.n_per_split);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + rr_off;
+          const int row = row_base + rr;
+          float v[4];
+          {
+            const uint32_t a = stg_addr + rr * 128 + ((cj ^ (rr & 7)) << 4);
+            uint32_t u0, u1, u2, u3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
+                         : "r"(a)
+                         : "memory");
+            v[0] = __uint_as_float(u0) + b4[0];
+            v[1] = __uint_as_float(u1) + b4[1];
+            v[2] = __uint_as_float(u2) + b4[2];
+            v[3] = __uint_as_float(u3) + b4[3];
+          }
+          if (row < p.M && col_ok) {
+            const long long o = static_cast<long long>(row) * p.ldo + ocol;
+            if constexpr (f32_resid) {
+              v[0] = xr[i].x + bf16_round(v[0]) * gt[i].x;
+              v[1] = xr[i].y + bf16_round(v[1]) * gt[i].y;
+              v[2] = xr[i].z + bf16_round(v[2]) * gt[i].z;
+              v[3] = xr[i].w + bf16_round(v[3]) * gt[i].w;
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) =
+                  make_float4(v[0], v[1], v[2], v[3]);
+            } else if constexpr (kEpi == OVB_EPI_F32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) =
+                  make_float4(v[0], v[1], v[2], v[3]);
             } else {
-              float* optr = reinterpret_cast<float*>(p.out) + obase + g * 8;
-              if (p.epilogue != OVB_EPI_F32) {
-                const float* rptr = reinterpret_cast<const float*>(p.resid) + static_cast<long long>(row) * p.ldr + col;
-                const float4 x0 = *reinterpret_cast<const float4*>(rptr);
-                const float4 x1 = *reinterpret_cast<const float4*>(rptr + 4);
-                float gt[8];
-                if (p.epilogue == OVB_EPI_GATE_RESID_F32) {
-                  const float4 g0 = *reinterpret_cast<const float4*>(gate_row + col);
-                  const float4 g1 = *reinterpret_cast<const float4*>(gate_row + col + 4);
-                  gt[0] = g0.x; gt[1] = g0.y; gt[2] = g0.z; gt[3] = g0.w;
-                  gt[4] = g1.x; gt[5] = g1.y; gt[6] = g1.z; gt[7] = g1.w;
-                } else {
+              if constexpr (kEpi == OVB_EPI_GELU_BF16) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) gt[j] = 1.0f;
-                }
-                const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = xr[j] + bf16_round(v[j]) * gt[j];
+                for (int j = 0; j < 4; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
+              } else if constexpr (kEpi == OVB_EPI_RESID_BF16) {
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].x));
+                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].y));
+                v[0] = bf16_round(v[0]) + f0.x; v[1] = bf16_round(v[1]) + f0.y;
+                v[2] = bf16_round(v[2]) + f1.x; v[3] = bf16_round(v[3]) + f1.y;
               }
-              *reinterpret_cast<float4*>(optr) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(optr + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              uint2 ov;
+              ov.x = pack_bf16x2(v[0], v[1]);
+              ov.y = pack_bf16x2(v[2], v[3]);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = ov;
             }
           }
         }
+        __syncwarp();  // staging buffer is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) mbar_arrive_cluster(leader_tempty0 + acc * 8);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -253,10 +307,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc_pair<512>(tmem_base);
   }
 }
 
@@ -309,7 +363,7 @@ extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(a->ldw) * 2};
-    const uint32_t box[2] = {kBK, kBN};
+    const uint32_t box[2] = {kBK, kBN / 2};
     int rc = encode_tmap_bf16(&tmB, a->W, 2, dims, strides, box);
     if (rc != OVB_OK) return rc;
   }
@@ -329,19 +383,32 @@ extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
   p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->M;
   p.n_per_split = a->N / n_split;
   p.out_split_stride = n_split > 1 ? a->out_split_stride : 0;
-  p.num_m_tiles = (a->M + kBM - 1) / kBM;
+  p.num_m_tiles = (a->M + 2 * kBM - 1) / (2 * kBM);
   p.num_n_tiles = (a->N + kBN - 1) / kBN;
 
   static bool attr_set = false;
   if (!attr_set) {
-    OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_RESID_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_GATE_RESID_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_RESID_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     attr_set = true;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = device_sm_count();
-  const int grid = num_tiles < sms ? num_tiles : sms;
-  gemm_bf16_kernel<<<grid, kGemmThreads, kGemmSmem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  const int pairs = sms / 2;
+  const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (a->epilogue) {
+    case OVB_EPI_BF16: gemm_bf16_kernel<OVB_EPI_BF16><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_GELU_BF16: gemm_bf16_kernel<OVB_EPI_GELU_BF16><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_RESID_F32: gemm_bf16_kernel<OVB_EPI_RESID_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_GATE_RESID_F32: gemm_bf16_kernel<OVB_EPI_GATE_RESID_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_F32: gemm_bf16_kernel<OVB_EPI_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
+    default: gemm_bf16_kernel<OVB_EPI_RESID_BF16><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
+  }
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OVB_OK;

@@ -61,6 +61,22 @@ def bench_gemm(M, N, K, res):
     res.append(r)
 
 
+def bench_gemm_resid(M, N, K, res):
+    """O-projection / FFN2 form: fp32 residual stream updated in place with a per-sample gate."""
+    a = torch.randn(M, K, device="cuda").to(bf16)
+    w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(bf16)
+    b = torch.randn(N, device="cuda").to(bf16)
+    x = torch.randn(M, N, device="cuda")
+    gate = torch.randn(1, N, device="cuda")
+    fl = 2.0 * M * N * K
+    med, _ = time_fn(lambda: ops.gemm(a, w, b, epilogue=ops.EPI_GATE_RESID_F32, out=x, resid=x, gate=gate,
+                                      rows_per_sample=M))
+    r = dict(kind="gemm_gate_resid_f32", M=M, N=N, K=K, ovb_ms=med, ovb_tflops=fl / med / 1e9)
+    print(f"gemm+gate+resid(fp32) {M}x{N}x{K}: ovb {med:.3f} ms {r['ovb_tflops']:.0f} TF/s "
+          f"(epilogue moves {M * N * 8 / 1e6:.0f} MB)", flush=True)
+    res.append(r)
+
+
 def bench_attn(L, H, Lk, res):
     q = torch.randn(1, L, H, 128, device="cuda").to(bf16)
     k = torch.randn(1, Lk, H, 128, device="cuda").to(bf16)
@@ -112,6 +128,8 @@ def main():
         shapes += [(8192, 8192, 8192), (L, 15360, 5120), (L, 5120, 5120), (L, 13824, 5120), (L, 5120, 13824)]
     for s in shapes:
         bench_gemm(*s, res)
+    bench_gemm_resid(L, 1536, 1536, res)
+    bench_gemm_resid(L, 1536, 8960, res)
     bench_attn(4096, 12, 4096, res)
     bench_attn(L, 12, L, res)
     bench_attn(L, 12, 512, res)

@@ -7,7 +7,8 @@
 #include "ptx.cuh"
 using namespace ovb;
 
-__global__ void __launch_bounds__(128, 1) k(int N, int iters, int per_commit, int hoist, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) k(int N, int iters, int per_commit, int mode, long long* cycles) {
+  const int hoist = 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -18,14 +19,15 @@ __global__ void __launch_bounds__(128, 1) k(int N, int iters, int per_commit, in
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tmem = slot;
   if (warp == 0 && elect_one()) {
-    const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(mode == 2 ? 64 : 128, N, 0, 0);
     const uint32_t sa = smem_u32(smem), sb = sa + 32768;
     const uint64_t da0 = umma_desc_sw128(sa, 16, 1024), db0 = umma_desc_sw128(sb, 16, 1024);
     uint32_t phase = 0;
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       for (int j = 0; j < per_commit; ++j) {
-        if (hoist) umma_ss(tmem, da0 + ((j & 3) * 2), db0 + ((j & 3) * 2), idesc, 1);
+        if (mode == 1) umma_ts(tmem, tmem + 256 + (j & 3) * 8, db0 + ((j & 3) * 2), idesc, 1);
+        else if (hoist) umma_ss(tmem, da0 + ((j & 3) * 2), db0 + ((j & 3) * 2), idesc, 1);
         else umma_ss(tmem, umma_desc_sw128(sa + (j & 3) * 32, 16, 1024), umma_desc_sw128(sb + (j & 3) * 32, 16, 1024), idesc, (i | j) != 0);
       }
       umma_commit(&bar);
@@ -42,8 +44,8 @@ __global__ void __launch_bounds__(128, 1) k(int N, int iters, int per_commit, in
 int main() {
   long long* dc; cudaMalloc(&dc, 148 * 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  printf("   N per_commit hoist | cycles/MMA  (tensor floor N/2)  TFLOP/s chip @1.9GHz\n");
-  for (int N : {64, 96, 128, 256}) for (int pc : {1, 2, 4, 8}) for (int hoist : {0, 1}) {
+  printf("mode 0=SS M128, 1=TS M128 (A in TMEM), 2=SS M64\n   N per_commit mode | cycles/MMA  (tensor floor N/2)  TFLOP/s chip @1.9GHz\n");
+  for (int hoist : {0, 1, 2}) for (int N : {32, 64, 128, 192, 256}) for (int pc : {8, 16}) {
     const int iters = 2048;
     for (int rep = 0; rep < 2; ++rep) k<<<148, 128, 100 * 1024>>>(N, iters, pc, hoist, dc);
     cudaError_t e = cudaDeviceSynchronize();
