@@ -21,10 +21,13 @@ What is printed (ONE JSON line, rank 0):
   cpu_baseline the oracle port of the reference path (oracle/dit.py) timed on this box's host
                cores on a bounded sample of the same workload.
 
-N>1 (torchrun): the token dimension is sharded over the ranks with Ulysses all-to-all
-(omni_video_b200/distributed), total work fixed => "scaling": "strong".  When the head count is
-not divisible by N (1.3B has 12 heads, N=8) the cond/uncond pair is split over two Ulysses groups
-of N/2 ranks and the two noise predictions are exchanged once per step.
+N>1 (torchrun), total work fixed => "scaling": "strong".  The step has two independent forwards
+(cond / uncond), so an even N first splits them over two groups of N/2 ranks that exchange the
+8.4 MB noise prediction once per step (no collective inside a forward); inside a
+group the token dimension is sharded with Ulysses all-to-all (omni_video_b200/distributed).
+N=2 -> cfg2, N=4 -> cfg2 x ulysses2, N=8 -> cfg2 x ulysses4 (12 heads % 8 != 0 rules out
+ulysses8 for the 1.3B model anyway).  `--no-cfg-split` gives the reference's layout (one Ulysses
+group of N ranks running both forwards).
 
 `--impl reference`: the reference's own implementation of this path is Python/PyTorch and ships
 no kernels; its CPU path (restated in oracle/dit.py and pinned to the reference's outputs by
@@ -211,7 +214,7 @@ def run_ours(args):
 
     # ---- parallel layout
     sp, cfg_par = world, 1
-    if world > 1 and heads % world != 0:
+    if world > 1 and (heads % world != 0 or args.cfg_split or (world % 2 == 0 and not args.no_cfg_split)):
         assert world % 2 == 0 and heads % (world // 2) == 0, f"{heads} heads cannot be split over {world} ranks"
         sp, cfg_par = world // 2, 2
     sp_group, cfg_groups = None, None
@@ -336,6 +339,10 @@ def run_ours(args):
                                     frac=round(whole_tf / world / peaks["tflops"], 4),
                                     tflop_per_step=round(2.0 * fl["total"] / 1e12, 1)))
 
+    vae = None
+    if not args.no_vae:
+        vae = vae_decode_leg((Fr, H, W), dev, peaks)
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_leg(cfg, (Fr, H, W), args.text_len, budget_s=args.cpu_budget)
@@ -353,11 +360,57 @@ def run_ours(args):
                 e2e=dict(value=round(args.steps / (e2e_ms / 1e3), 5), unit="steps/s",
                          h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=int(launches), clocks=clk, roofline=roofline)
+    if vae is not None:
+        line["vae_decode"] = vae
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def vae_decode_leg(grid_lat, dev, peaks):
+    """BASELINE.json configs[1] ends with one Wan2.1 VAE decode of the sampled latent (rank 0, as in
+    x2x_gen_unified.py:512-524).  Reported beside the step rate, not folded into it: one decode per
+    50 steps.  Algorithmic FLOPs: SURVEY.md Appendix A cost model (measured on the reference with
+    FlopCounterMode): 0.688 GFLOP per latent pixel for frame 0 + 2.162 per later frame, plus the
+    per-frame single-head attention."""
+    import torch
+    from omni_video_b200 import ops
+    from omni_video_b200.modules.vae2_1 import Wan2_1_VAE
+    torch.cuda.empty_cache()
+    T, h, w = grid_lat
+    vae = Wan2_1_VAE(vae_pth=None, device=dev)
+    g = torch.Generator(device="cuda").manual_seed(1818)
+    for name, p in vae.model.named_parameters():
+        if p.dim() > 1 and "gamma" not in name:
+            p.data.copy_(torch.randn(p.shape, generator=g, device="cuda") / p[0].numel() ** 0.5)
+    z = torch.randn((16, T, h, w), generator=g, device=dev)
+    flops = (0.688e9 + 2.162e9 * (T - 1)) * h * w + 4.0 * (h * w) ** 2 * 384 * T
+    times = []
+    for it in range(3):
+        ops.timeline = [] if it == 2 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = vae.decode([z])[0]
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    tl, ops.timeline = ops.timeline, None
+    conv_fl = sum(t[1] for t in tl if t[0] == "conv")
+    conv_ms = sum(t[3].elapsed_time(t[4]) for t in tl if t[0] == "conv")
+    norm_b = sum(t[1] for t in tl if t[0] == "norm")
+    norm_ms = sum(t[3].elapsed_time(t[4]) for t in tl if t[0] == "norm")
+    ms = min(times[1:])
+    res = dict(ms=round(ms, 1), out_shape=list(out.shape), tflops=round(flops / ms / 1e9, 1),
+               frac_of_bf16_peak=round(flops / ms / 1e9 / peaks["tflops"], 4),
+               conv_kernel=dict(tflops=round(conv_fl / max(conv_ms, 1e-9) / 1e9, 1), share=round(conv_ms / ms, 3)),
+               norm_kernel=dict(gbs=round(norm_b / max(norm_ms, 1e-9) / 1e6, 1), share=round(norm_ms / ms, 3),
+                                frac_of_hbm_peak=round(norm_b / max(norm_ms, 1e-9) / 1e6 / peaks["hbm"], 4)),
+               finite=bool(torch.isfinite(out).all().item()))
+    del out, vae
+    torch.cuda.empty_cache()
+    return res
 
 
 # --------------------------------------------------------------------------------- CPU legs
@@ -453,6 +506,13 @@ def main():
     ap.add_argument("--video", default="480p", choices=sorted(VIDEOS))
     ap.add_argument("--text-len", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
+    ap.add_argument("--no-cfg-split", action="store_true",
+                    help="N>1: one Ulysses group of N ranks running cond then uncond (the reference's layout) "
+                         "instead of the default cond/uncond split over two groups of N/2")
+    ap.add_argument("--cfg-split", action="store_true",
+                    help="N>1: put the cond/uncond forwards on two Ulysses groups of N/2 ranks even when "
+                         "the head count would allow one group of N (what N=8 does for 12 heads)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.impl == "reference":

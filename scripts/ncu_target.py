@@ -1,0 +1,52 @@
+"""Small single-kernel targets for `ncu --set full` captures.
+    python scripts/ncu_target.py attn|gemm|gemm_resid|conv96|conv192|norm
+"""
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from omni_video_b200 import ops, vae_ops  # noqa: E402
+
+bf16 = torch.bfloat16
+what = sys.argv[1] if len(sys.argv) > 1 else "attn"
+torch.manual_seed(0)
+if what == "attn":
+    L, H = 32760, 12
+    q, k, v = (torch.randn(1, L, H, 128, device="cuda").to(bf16) for _ in range(3))
+    out = torch.empty_like(q)
+    fn = lambda: ops.attention(q, k, v, out=out)  # noqa: E731
+elif what in ("gemm", "gemm_resid"):
+    M, N, K = 32760, 1536, 1536
+    a = torch.randn(M, K, device="cuda").to(bf16)
+    w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(bf16)
+    b = torch.randn(N, device="cuda").to(bf16)
+    if what == "gemm":
+        o = torch.empty(M, N, device="cuda", dtype=bf16)
+        fn = lambda: ops.gemm(a, w, b, out=o)  # noqa: E731
+    else:
+        x = torch.randn(M, N, device="cuda")
+        g = torch.randn(1, N, device="cuda")
+        fn = lambda: ops.gemm(a, w, b, epilogue=ops.EPI_GATE_RESID_F32, out=x, resid=x, gate=g, rows_per_sample=M)  # noqa: E731
+elif what in ("conv96", "conv192"):
+    c = 96 if what == "conv96" else 192
+    T, H, W = (9, 480, 832) if c == 96 else (9, 240, 416)
+    x = torch.randn(T, H, W, c, device="cuda").to(bf16)
+    wt = torch.randn(c, c, 3, 3, 3, device="cuda") / math.sqrt(27 * c)
+    pc = vae_ops.pack_conv3d(wt, torch.zeros(c, device="cuda"))
+    fn = lambda: vae_ops.conv3d(x, pc, (T, H, W))  # noqa: E731
+else:
+    x = torch.randn(9 * 480 * 832, 96, device="cuda").to(bf16)
+    g = torch.ones(96, device="cuda")
+    fn = lambda: vae_ops.rmsnorm_silu(x, g)  # noqa: E731
+for _ in range(3):
+    fn()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+fn()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("ok", what)
