@@ -164,8 +164,9 @@ def init_random_(model, seed: int):
 class Stepper:
     """The reference's per-timestep work (x2x_gen_unified.py:474-492) on our WanModel."""
 
-    def __init__(self, model, seq_len, world, rank, cfg_groups):
+    def __init__(self, model, seq_len, world, rank, cfg_groups, batch_cfg=False):
         import torch
+        self.batch_cfg = batch_cfg
         self.torch, self.model, self.seq_len = torch, model, seq_len
         self.world, self.rank = world, rank
         self.cfg_groups = cfg_groups  # None, or (my_branch, pair_group) when cond/uncond are split
@@ -174,7 +175,13 @@ class Stepper:
     def step(self, latent, ctx_c, ctx_u, i):
         torch = self.torch
         t = torch.full((1,), int(self.sigmas[i % 50] * 1000), device=latent.device, dtype=torch.int64)
-        if self.cfg_groups is None:
+        if self.cfg_groups is None and self.batch_cfg:
+            # cond + uncond as ONE forward with B = 2 (WanModel.forward takes lists): same
+            # arithmetic per sample, half the launches, and 2x the CTAs per attention launch
+            # (12 heads x 128 query blocks = 10.4 waves of 148 SMs -> 20.8: less tail waste)
+            cond, uncond = self.model([latent, latent], t=torch.cat([t, t]), context=[ctx_c, ctx_u],
+                                      seq_len=self.seq_len)
+        elif self.cfg_groups is None:
             cond = self.model([latent], t=t, context=[ctx_c], seq_len=self.seq_len)[0]
             uncond = self.model([latent], t=t, context=[ctx_u], seq_len=self.seq_len)[0]
         else:
@@ -245,7 +252,8 @@ def run_ours(args):
     latent0 = torch.randn((16, Fr, H, W), generator=gen, device=dev, dtype=torch.float32)
     ctx_c = torch.randn((min(512, args.text_len), 4096), generator=gen, device=dev).to(torch.bfloat16)
     ctx_u = torch.randn((min(512, args.text_len), 4096), generator=gen, device=dev).to(torch.bfloat16)
-    stepper = Stepper(model, seq_len, world, rank, cfg_groups)
+    stepper = Stepper(model, seq_len, world, rank, cfg_groups,
+                      batch_cfg=(sp == 1 and cfg_par == 1 and not args.no_cfg_batch))
 
     def barrier():
         if world > 1:
@@ -354,6 +362,7 @@ def run_ours(args):
                 config=dict(workload=f"OmniVideo2-{args.model} DiT, {args.video} "
                                      f"(latent 16x{Fr}x{H}x{W}, {L} tokens), text_len {args.text_len}, "
                                      "step = cond+uncond forward + CFG + flow update, random-init weights",
+                            cfg_batched=bool(stepper.batch_cfg),
                             parallelism=(f"ulysses{sp}" + (f"xcfg{cfg_par}" if cfg_par > 1 else "")) if world > 1 else "single",
                             l2="inputs+weights per step (>2.8 GB) exceed the 126 MB L2; no flush needed",
                             forwards_per_s=round(2 * steps_per_s, 5), finite=finite),
@@ -507,6 +516,8 @@ def main():
     ap.add_argument("--text-len", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
+    ap.add_argument("--no-cfg-batch", action="store_true",
+                    help="N=1: run cond and uncond as two B=1 forwards (the reference's loop) instead of one B=2 forward")
     ap.add_argument("--no-cfg-split", action="store_true",
                     help="N>1: one Ulysses group of N ranks running cond then uncond (the reference's layout) "
                          "instead of the default cond/uncond split over two groups of N/2")
