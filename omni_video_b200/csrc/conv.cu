@@ -12,10 +12,17 @@
 // causal (left-only) temporal padding.  The box lands in shared memory as 128 rows x KC channels,
 // K-major with the hardware swizzle, i.e. exactly the tcgen05.mma A-operand layout.
 //
-// Same warp-specialised persistent structure as gemm.cu (TMA producer warp, single-thread MMA
-// issuer, TMEM allocator warp, 4 epilogue warps; two TMEM accumulators so the epilogue of tile i
-// overlaps the main loop of tile i+1); tile width BN, channel chunk KC (64/32/16 -> 128/64/32-byte
-// swizzle) and the ring depth are runtime parameters so one kernel serves every layer of the VAE
+// Same warp-specialised persistent structure as gemm.cu, on CTA PAIRS (tcgen05.mma.cta_group::2,
+// M = 256): the two CTAs of a cluster take two consecutive M tiles (two voxel boxes) of the same N
+// tile; each loads its own A box and only HALF of the weight rows, which halves the B-operand bytes
+// an SM streams from shared memory per MMA (the measured limiter at these tile widths, see
+// gemm.cu).  Warp 0 issues the A loads, warp 3 the B loads (TMA issue from one thread costs
+// ~80 cycles per load plus ~250 per barrier round trip — scripts/microbench/tma_rate.cu — so two
+// issuing threads and one stage per TAP (all channel chunks of a tap together, when they fit)
+// keep the producer ahead of the tensor pipe); warp 1 of the leader issues the MMAs, warp 2
+// owns TMEM (two accumulators, epilogue of tile i overlaps the main loop of tile i+1), warps 4-7
+// run the epilogue.  Tile width BN, channel chunk KC (64/32/16 -> 128/64/32-byte swizzle), chunks
+// per stage and ring depth are runtime parameters so one kernel serves every layer of the VAE
 // (Cin, Cout in {16, 32, 96, 192, 384, 768} and the 3-channel head).
 //
 // The output address of voxel (t, h, w), channel n is
@@ -34,6 +41,7 @@ constexpr int kConvThreads = 256;
 constexpr int kConvMaxStages = 8;
 constexpr int kConvMaxTaps = 27;
 constexpr int kConvSmemBudget = 225 * 1024;
+constexpr int kConvStagingBytes = 4 * 32 * 32 * 4;
 
 struct ConvParams {
   int To, Ho, Wo;
@@ -41,9 +49,10 @@ struct ConvParams {
   int n_wt, n_ht;
   int st, sh, sw;
   int Cin, KC, n_kc;
+  int kc_per_stage, a_chunk_bytes, b_chunk_bytes;
   int n_taps;
   int Cout, BN, n_nt;
-  int stages, stage_bytes, a_bytes;
+  int stages, stage_bytes;
   const float* bias;
   void* out;
   const __nv_bfloat16* resid;
@@ -55,13 +64,14 @@ struct ConvParams {
   signed char dt[kConvMaxTaps], dh[kConvMaxTaps], dw[kConvMaxTaps];
 };
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  float* staging = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes + kConvStagingBytes);
   uint64_t* empty_bar = full_bar + kConvMaxStages;
   uint64_t* tfull_bar = empty_bar + kConvMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -69,10 +79,16 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
   const int m_tiles = p.To * p.n_ht * p.n_wt;
-  const int num_tiles = m_tiles * p.n_nt;
-  const int num_ks = p.n_taps * p.n_kc;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int num_tiles = m_pairs * p.n_nt;  // pair tiles (256 voxels x BN)
+  const int stages_per_tap = p.n_kc / p.kc_per_stage;
+  const int num_ks = p.n_taps * stages_per_tap;
   const int bw = 1 << p.bw_log2;
+  const int a_stage_bytes = p.kc_per_stage * p.a_chunk_bytes;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -80,46 +96,72 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);  // leader's A producer + leader's B producer (expect_tx each)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    // elect.sync (not `lane == 0`): the compiler then knows exactly one lane runs the loop and
-    // feeds UTMALDG / UTCHMMA from uniform registers without a per-instruction waterfall loop
+    // ------------------------------------------------------------ A producer (both CTAs)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = static_cast<uint32_t>(128 * p.KC * 2 + p.BN * p.KC * 2);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_nt;
-        int m = tile / p.n_nt;
+      const uint32_t tx = static_cast<uint32_t>(2 * p.kc_per_stage * 128 * p.KC * 2);
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m = (tile / p.n_nt) * 2 + static_cast<int>(rank);
+        const bool real = m < m_tiles;
         const int wt = m % p.n_wt;
         m /= p.n_wt;
         const int ht = m % p.n_ht;
-        const int t = m / p.n_ht;
+        const int t = real ? m / p.n_ht : p.To + 4;  // odd tail: a box fully outside -> zero fill
         const int w0 = (wt << p.bw_log2) * p.sw, h0 = ht * p.bh * p.sh, t0 = t * p.st;
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const int ct = t0 + p.dt[tap], ch = h0 + p.dh[tap], cw = w0 + p.dw[tap];
-          for (int kc = 0; kc < p.n_kc; ++kc) {
+          for (int g = 0; g < stages_per_tap; ++g) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * p.stage_bytes;
-            uint8_t* sb = sa + p.a_bytes;
-            mbar_expect_tx(&full_bar[stage], tx);
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * p.KC, cw, ch, ct);
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + kc * p.KC, nt * p.BN);
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+            for (int q = 0; q < p.kc_per_stage; ++q)
+              tma_load_4d_pair(sa + q * p.a_chunk_bytes, &tmA, leader_full,
+                               (g * p.kc_per_stage + q) * p.KC, cw, ch, ct);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ B producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int half = p.BN >> 1;
+      const uint32_t tx = static_cast<uint32_t>(2 * p.kc_per_stage * half * p.KC * 2);
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int nt = tile % p.n_nt;
+        const int wrow0 = nt * p.BN + static_cast<int>(rank) * half;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          for (int g = 0; g < stages_per_tap; ++g) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sb = smem + stage * p.stage_bytes + a_stage_bytes;
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+            for (int q = 0; q < p.kc_per_stage; ++q)
+              tma_load_2d_pair(sb + q * p.b_chunk_bytes, &tmB, leader_full,
+                               tap * p.Cin + (g * p.kc_per_stage + q) * p.KC, wrow0);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -129,16 +171,16 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(256, p.BN, 0, 0);
       const uint32_t row_bytes = p.KC * 2;
       const int k_steps = p.KC / 16;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -146,13 +188,16 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
-          const uint32_t sb = sa + p.a_bytes;
-          for (int k = 0; k < k_steps; ++k) {
-            umma_ss(d_tmem, umma_desc_kmajor(sa + k * 32, row_bytes),
-                    umma_desc_kmajor(sb + k * 32, row_bytes), idesc, (ks | k) != 0);
+          const uint32_t sb = sa + a_stage_bytes;
+          for (int q = 0; q < p.kc_per_stage; ++q) {
+            for (int k = 0; k < k_steps; ++k) {
+              umma_ss_pair(d_tmem, umma_desc_kmajor(sa + q * p.a_chunk_bytes + k * 32, row_bytes),
+                           umma_desc_kmajor(sb + q * p.b_chunk_bytes + k * 32, row_bytes), idesc,
+                           (ks | q | k) != 0);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (ks == num_ks - 1) umma_commit(&tfull_bar[acc]);
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (ks == num_ks - 1) umma_commit_pair(&tfull_bar[acc], 3);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -165,86 +210,160 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue (both CTAs)
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // accumulator row = voxel inside the box
-    const int hl = r >> p.bw_log2, wl = r & (bw - 1);
+    const uint32_t stg_addr = smem_u32(staging + quad * (32 * 32));
+    const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    const int rr_off = lane >> 3, cj = lane & 7;
+    const bool transposed = p.out_mode == OVB_CONV_OUT_BF16 && (p.BN & 31) == 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int nt = tile % p.n_nt;
-      int m = tile / p.n_nt;
+      int m = (tile / p.n_nt) * 2 + static_cast<int>(rank);
+      const bool real = m < m_tiles;
       const int wt = m % p.n_wt;
       m /= p.n_wt;
       const int ht = m % p.n_ht;
       const int t = m / p.n_ht;
-      const int h = ht * p.bh + hl, w = (wt << p.bw_log2) + wl;
-      const bool ok = h < p.Ho && w < p.Wo;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const long long vox = p.out_base + t * p.os_t + h * p.os_h + w * p.os_w;
-      const int n_chunks = p.BN / 16;
+      if (transposed) {
+        // 32-column chunks through a swizzled shared-memory transpose (as in gemm.cu): in the read
+        // phase 8 lanes cover 64 contiguous output bytes of one voxel and a warp instruction 4
+        // voxels, instead of 32 voxels x 32 bytes
+        const int n_chunks = p.BN / 32;
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        const int n0 = nt * p.BN + c * 16;
-        if (n0 >= p.Cout) break;  // warp-uniform
-        uint32_t v[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + c * 16, v);
-        tmem_wait_ld();
-        if (ok) {
-        float f[16];
+        for (int c = 0; c < n_chunks; ++c) {
+          const int n0 = nt * p.BN + c * 32;
+          if (n0 >= p.Cout) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + c * 32, v);
+          const int col = n0 + cj * 4;
+          const bool col_ok = col < p.Cout;
+          const int grp = col / p.n_group;
+          const long long coff = grp * p.group_stride + (col - grp * p.n_group);
+          // this lane's 8 voxels of the read phase and their residual values, requested up front
+          long long voff[8];
+          uint2 xb[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
+          for (int i = 0; i < 8; ++i) {
+            const int rr = quad * 32 + 4 * i + rr_off;
+            const int h = ht * p.bh + (rr >> p.bw_log2), w = (wt << p.bw_log2) + (rr & (bw - 1));
+            const bool ok = real && col_ok && h < p.Ho && w < p.Wo;
+            voff[i] = ok ? p.out_base + t * p.os_t + h * p.os_h + w * p.os_w + coff : -1;
+            xb[i] = make_uint2(0u, 0u);
+            if (ok && p.resid != nullptr) xb[i] = *reinterpret_cast<const uint2*>(p.resid + voff[i]);
+          }
+          float b4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.bias != nullptr && col_ok) {
+            const float4 bv = *reinterpret_cast<const float4*>(p.bias + col);
+            b4[0] = bv.x; b4[1] = bv.y; b4[2] = bv.z; b4[3] = bv.w;
+          }
+          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + j < p.Cout) f[j] += __ldg(p.bias + n0 + j);
-        }
-        if (p.out_mode == OVB_CONV_OUT_BF16) {
-          const int grp = p.n_group > 0 ? n0 / p.n_group : 0;
-          const long long off = vox + grp * p.group_stride + (n0 - grp * p.n_group);
-          if (p.resid != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + off);
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = stg_addr + lane * 128 + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(v[4 * j]),
+                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+          }
+          __syncwarp();
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint4 rv = rp[g];
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 a = __bfloat1622float2(r2[j]);
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + rr_off;
+            const uint32_t a = stg_addr + rr * 128 + ((cj ^ (rr & 7)) << 4);
+            uint32_t u0, u1, u2, u3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
+                         : "r"(a)
+                         : "memory");
+            float f0 = __uint_as_float(u0) + b4[0], f1 = __uint_as_float(u1) + b4[1];
+            float f2 = __uint_as_float(u2) + b4[2], f3 = __uint_as_float(u3) + b4[3];
+            if (voff[i] >= 0) {
+              if (p.resid != nullptr) {
+                const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].x));
+                const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].y));
                 // conv result is stored as bf16 before the add in the unfused formulation
-                f[g * 8 + 2 * j] = bf16_round(f[g * 8 + 2 * j]) + a.x;
-                f[g * 8 + 2 * j + 1] = bf16_round(f[g * 8 + 2 * j + 1]) + a.y;
+                f0 = bf16_round(f0) + a0.x; f1 = bf16_round(f1) + a0.y;
+                f2 = bf16_round(f2) + a1.x; f3 = bf16_round(f3) + a1.y;
+              }
+              uint2 o;
+              o.x = pack_bf16x2(f0, f1);
+              o.y = pack_bf16x2(f2, f3);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + voff[i]) = o;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        const int hl = r >> p.bw_log2, wl = r & (bw - 1);
+        const int h = ht * p.bh + hl, w = (wt << p.bw_log2) + wl;
+        const bool ok = real && h < p.Ho && w < p.Wo;
+        const long long vox = p.out_base + t * p.os_t + h * p.os_h + w * p.os_w;
+        const int n_chunks = p.BN / 16;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          const int n0 = nt * p.BN + c * 16;
+          if (n0 >= p.Cout) break;  // warp-uniform
+          uint32_t v[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + c * 16, v);
+          tmem_wait_ld();
+          if (ok) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + j < p.Cout) f[j] += __ldg(p.bias + n0 + j);
+            }
+            if (p.out_mode == OVB_CONV_OUT_BF16) {
+              const int grp = n0 / p.n_group;
+              const long long off = vox + grp * p.group_stride + (n0 - grp * p.n_group);
+              if (p.resid != nullptr) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.resid + off);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                  const uint4 rv = rp[g];
+                  const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 a = __bfloat1622float2(r2[j]);
+                    f[g * 8 + 2 * j] = bf16_round(f[g * 8 + 2 * j]) + a.x;
+                    f[g * 8 + 2 * j + 1] = bf16_round(f[g * 8 + 2 * j + 1]) + a.y;
+                  }
+                }
+              }
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                uint4 o;
+                o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+                o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+                o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+                o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+                op[g] = o;
+              }
+            } else {  // OVB_CONV_OUT_F32_PLANAR(_CLAMP): out[n][t][h][w]
+              float* op = reinterpret_cast<float*>(p.out) + vox;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (n0 + j < p.Cout) {
+                  float y = f[j];
+                  if (p.out_mode == OVB_CONV_OUT_F32_PLANAR_CLAMP) y = fminf(fmaxf(y, -1.0f), 1.0f);
+                  op[(n0 + j) * p.plane_stride] = y;
+                }
               }
             }
           }
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 o;
-            o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-            o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-            o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-            o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-            op[g] = o;
-          }
-        } else {  // OVB_CONV_OUT_F32_PLANAR(_CLAMP): out[n][t][h][w]
-          float* op = reinterpret_cast<float*>(p.out) + vox;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (n0 + j < p.Cout) {
-              float y = f[j];
-              if (p.out_mode == OVB_CONV_OUT_F32_PLANAR_CLAMP) y = fminf(fmaxf(y, -1.0f), 1.0f);
-              op[(n0 + j) * p.plane_stride] = y;
-            }
-          }
+          __syncwarp();
         }
-        }  // ok
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) mbar_arrive_cluster(leader_tempty0 + acc * 8);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -253,10 +372,10 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc_pair<512>(tmem_base);
   }
 }
 
@@ -334,9 +453,21 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
     p.BN = bn;
     p.n_nt = (a->w_rows + bn - 1) / bn;
   }
-  p.a_bytes = 128 * p.KC * 2;
-  p.stage_bytes = (p.a_bytes + p.BN * p.KC * 2 + 1023) / 1024 * 1024;
-  p.stages = (kConvSmemBudget - 2048) / p.stage_bytes;
+  OVB_CHECK_ARG(p.BN >= 16 && p.BN % 16 == 0, "ovb_conv3d: no valid N tile for Cout=%d", a->Cout);
+  // ---- shared-memory ring: one stage holds `kc_per_stage` channel chunks of one tap
+  p.a_chunk_bytes = 128 * p.KC * 2;                                       // multiple of 4096
+  p.b_chunk_bytes = ((p.BN / 2) * p.KC * 2 + 1023) / 1024 * 1024;
+  const int chunk_bytes = p.a_chunk_bytes + p.b_chunk_bytes;
+  const int ring_budget = kConvSmemBudget - kConvStagingBytes - 2048;
+  p.kc_per_stage = 1;
+  for (int q = p.n_kc; q >= 1; --q) {  // largest divisor of n_kc that still leaves >= 4 stages
+    if (p.n_kc % q == 0 && q * chunk_bytes * 4 <= ring_budget) {
+      p.kc_per_stage = q;
+      break;
+    }
+  }
+  p.stage_bytes = p.kc_per_stage * chunk_bytes;
+  p.stages = ring_budget / p.stage_bytes;
   if (p.stages > kConvMaxStages) p.stages = kConvMaxStages;
   OVB_CHECK_ARG(p.stages >= 2, "ovb_conv3d: tile does not fit shared memory (BN=%d KC=%d)", p.BN, p.KC);
   p.bias = a->bias;
@@ -367,12 +498,12 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->n_taps) * a->Cin, static_cast<uint64_t>(a->w_rows)};
     const uint64_t strides[1] = {static_cast<uint64_t>(a->n_taps) * a->Cin * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.BN)};
+    const uint32_t box[2] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.BN / 2)};
     int rc = encode_tmap_bf16_ex(&tmB, a->w, 2, dims, strides, box, nullptr, p.KC * 2);
     if (rc != OVB_OK) return rc;
   }
 
-  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 512;
+  const int smem_bytes = p.stages * p.stage_bytes + kConvStagingBytes + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     OVB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel,
@@ -380,10 +511,11 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
                                         kConvSmemBudget + 2048));
     attr_set = true;
   }
-  const long long num_tiles = static_cast<long long>(p.To) * p.n_ht * p.n_wt * p.n_nt;
-  OVB_CHECK_ARG(num_tiles < (1ll << 31), "ovb_conv3d: too many tiles");
-  const int sms = device_sm_count();
-  const int grid = num_tiles < sms ? static_cast<int>(num_tiles) : sms;
+  const long long m_tiles = static_cast<long long>(p.To) * p.n_ht * p.n_wt;
+  const long long num_tiles = ((m_tiles + 1) / 2) * p.n_nt;  // pair tiles
+  OVB_CHECK_ARG(m_tiles < (1ll << 30) && num_tiles < (1ll << 30), "ovb_conv3d: too many tiles");
+  const int pairs = device_sm_count() / 2;
+  const int grid = 2 * (num_tiles < pairs ? static_cast<int>(num_tiles) : pairs);
   conv3d_igemm_kernel<<<grid, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) rmsnorm_silu_cl_kernel(const __nv_bfloat1
                                                                const float* __restrict__ gamma,
                                                                __nv_bfloat16* __restrict__ out,
                                                                long long n_vox, int C, int silu) {
+  constexpr int kU = MAXC >= 2 ? 2 : 4;  // voxels per group per iteration: 16-byte loads in flight per lane
   const int lane = threadIdx.x & (LPV - 1);
   constexpr int kGroupsPerWarp = 32 / LPV;
   const int sub = (threadIdx.x & 31) / LPV;
@@ -34,49 +35,73 @@ __global__ void __launch_bounds__(256) rmsnorm_silu_cl_kernel(const __nv_bfloat1
   const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int chunks_all = C >> 3;
   const float sqrt_c = sqrtf(static_cast<float>(C));
+  constexpr int kVoxPerWarp = kGroupsPerWarp * kU;
+  // gamma chunks of this lane stay in registers for the whole kernel
+  float g[MAXC][8];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + i * LPV;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[i][j] = c < chunks_all ? gamma[c * 8 + j] : 0.f;
+  }
   // warp-uniform trip count: the shuffles below need all 32 lanes
-  for (long long v0 = warp_id * kGroupsPerWarp; v0 < n_vox; v0 += n_warps * kGroupsPerWarp) {
-    const long long v = v0 + sub;
-    const int chunks = v < n_vox ? chunks_all : 0;
-    const uint4* src = reinterpret_cast<const uint4*>(x + v * C);
-    uint4 raw[MAXC];
-    float ss = 0.f;
+  for (long long v0 = warp_id * kVoxPerWarp; v0 < n_vox; v0 += n_warps * kVoxPerWarp) {
+    uint4 raw[kU][MAXC];
+    int chunks[kU];
+    // all loads of the iteration first: kU * MAXC independent 16-byte requests per lane
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + i * LPV;
-      if (c < chunks) {
-        raw[i] = src[c];
-        float f[8];
-        unpack8(raw[i], f);
+    for (int u = 0; u < kU; ++u) {
+      const long long v = v0 + u * kGroupsPerWarp + sub;
+      chunks[u] = v < n_vox ? chunks_all : 0;
+      const uint4* src = reinterpret_cast<const uint4*>(x + v * C);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+      for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + i * LPV;
+        raw[u][i] = make_uint4(0u, 0u, 0u, 0u);
+        if (c < chunks[u]) raw[u][i] = src[c];
       }
     }
 #pragma unroll
-    for (int o = LPV / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
-    uint4* dst = reinterpret_cast<uint4*>(out + v * C);
+    for (int u = 0; u < kU; ++u) {
+      const long long v = v0 + u * kGroupsPerWarp + sub;
+      float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + i * LPV;
-      if (c < chunks) {
+      for (int i = 0; i < MAXC; ++i) {
         float f[8];
-        unpack8(raw[i], f);
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + c * 8);
-        const float4 g1 = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        unpack8(raw[u][i], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float y = f[j] * inv * g[j];
-          if (silu) y = y / (1.0f + __expf(-y));
-          f[j] = y;
+        for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+      }
+#pragma unroll
+      for (int o = LPV / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+      uint4* dst = reinterpret_cast<uint4*>(out + v * C);
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + i * LPV;
+        if (c < chunks[u]) {
+          float f[8];
+          unpack8(raw[u][i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float y = f[j] * inv * g[i][j];
+            // SiLU(y) = y * sigmoid(y) = h + h * tanh(h), h = y/2: one MUFU op and no division
+            // (tanh.approx relative error ~2^-11, below the bf16 rounding of the result)
+            if (silu) {
+              const float h = 0.5f * y;
+              float th;
+              asm("tanh.approx.f32 %0, %1;\n" : "=f"(th) : "f"(h));
+              y = fmaf(h, th, h);
+            }
+            f[j] = y;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]);
+          o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]);
+          o.w = pack_bf16x2(f[6], f[7]);
+          dst[c] = o;
         }
-        uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]);
-        o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]);
-        o.w = pack_bf16x2(f[6], f[7]);
-        dst[c] = o;
       }
     }
   }

@@ -33,3 +33,15 @@ if has ncu; then
       -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
 fi
+if has ncuk; then
+  # single-kernel full captures (scripts/ncu_target.py): attention, GEMM (+fp32 residual epilogue), VAE conv, VAE norm
+  for k in attn gemm gemm_resid conv96 conv192 norm; do
+    python scripts/ncu_target.py $k > gpurun_out/plain_$k.log 2>&1 &&
+    ncu --set full --clock-control none --import-source on --profile-from-start off -f \
+        -o gpurun_out/prof_$k python scripts/ncu_target.py $k > gpurun_out/ncu_$k.log 2>&1
+    echo "ncu $k rc=$?"
+  done
+fi
+if has vae; then
+  python scripts/gpu_vae_bench.py --video 480p --encode 2>&1 | tee gpurun_out/vae_bench_480p.log | head -30
+fi
