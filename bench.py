@@ -333,9 +333,19 @@ def run_ours(args):
     fl = forward_flops(cfg, L, args.text_len)
     steps_per_s = args.steps / (dev_ms / 1e3)
     whole_tf = 2.0 * fl["total"] * steps_per_s / 1e12
+    traffic = None
+    try:  # per-launch DRAM bytes of the self-attention launch from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tj = json.load(fh)["attn_fwd_kernel"]
+        key = f"B1_H{heads // sp}_Lq{seq_len}_Lk{seq_len}"
+        traffic = tj.get(key)
+    except Exception:
+        traffic = None
     roofline = dict(bound="tensor", kernel="attn_fwd_kernel (self+cross flash attention, tcgen05)",
                     achieved=round(attn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
-                    frac=round(attn_tf / peaks["tflops"], 4), traffic=None,
+                    frac=round(attn_tf / peaks["tflops"], 4), traffic=traffic,
+                    traffic_note="DRAM bytes of one self-attention launch (ncu --set full, profiles/); "
+                                 "algorithmic q+k+v+o bytes are the same 402.6 MB",
                     peak_source=peaks["source"],
                     launches=agg.get("attn", [0, 0, 0])[2],
                     ms_per_launch=round(agg["attn"][1] / max(1, agg["attn"][2]), 4) if "attn" in agg else None,
