@@ -22,6 +22,8 @@
 //
 // Algorithmic bytes per tile are tiny next to the FLOPs (arithmetic intensity >= 700 FLOP/B for
 // the smallest DiT shape), so the bounding roofline is the tensor pipe; see DESIGN.md §3.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -314,6 +316,262 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fp32-residual epilogues with TMA on both sides of the residual stream:
+//     out(fp32) = resid(fp32) + bf16(acc + bias) * gate            (reference model.py:246, :250, :254)
+// The residual stream costs 8 bytes per output element (403 MB per [32760,1536] GEMM), all of it
+// latency-bound when four epilogue warps fetch it with ordinary loads (16 KB in flight per SM).
+// Here one epilogue thread runs a 4-deep ring of [128 rows x 32 columns] fp32 boxes: TMA loads the
+// residual box two chunks ahead, each thread reads ITS row from the box (TMA's 128-byte swizzle is
+// conflict free for row-per-thread 16-byte accesses), writes the result back in place, and the box
+// goes to `out` with one TMA store.  Main loop as above with a 4-stage operand ring.
+constexpr int kRStages = 4;                       // operand ring
+constexpr int kRing = 4;                          // residual boxes
+constexpr int kRBoxBytes = kBM * 32 * 4;          // 16 KB
+constexpr int kGemmResidSmem = kRStages * kStageBytes + kRing * kRBoxBytes + 1024 + 256;
+
+template <bool kGate>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_resid_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                      const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = smem + kRStages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + kRing * kRBoxBytes);
+  uint64_t* empty_bar = full_bar + kRStages;
+  uint64_t* tfull_bar = empty_bar + kRStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* rfull_bar = tempty_bar + 2;  // [kRing] residual box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + kRing);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int kb_per_split = (p.k_per_split + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kRStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);
+    }
+    for (int b = 0; b < kRing; ++b) mbar_init(&rfull_bar[b], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        const int row0 = m_tile * 2 * kBM + rank * kBM;
+        const int wrow0 = n_tile * kBN + rank * (kBN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
+          const int split = kb / kb_per_split;
+          const int kcol = (kb - split * kb_per_split) * kBK;
+          tma_load_3d_pair(sa, &tmA, leader_full, kcol, row0, split);
+          tma_load_2d_pair(sb, &tmB, leader_full, kb * kBK, wrow0);
+          if (++stage == kRStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(2 * kBM, kBN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_ss_pair(d_tmem, umma_desc_sw128(sa + k * 32, 16, 1024),
+                         umma_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb | k) != 0);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc], 3);
+          if (++stage == kRStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (both CTAs)
+    const int quad = warp & 3;
+    const int r_in_cta = quad * 32 + lane;             // this thread's row of the CTA's 128
+    const bool leader_thread = warp == 4 && lane == 0;  // runs the residual ring
+    const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    constexpr int kChunks = kBN / 32;
+    constexpr int kAhead = 2;  // residual boxes requested ahead of the one being processed
+    // number of 32-column chunks this CTA will process, in order (tiles x chunks that start < N)
+    const int chunks_per_tile_full = kChunks;
+    auto tile_of = [&](int it) { return pair + it * num_pairs; };
+    auto chunk_coords = [&](long long g, int& row0, int& col0) -> bool {
+      const int it = static_cast<int>(g / chunks_per_tile_full);
+      const int c = static_cast<int>(g - static_cast<long long>(it) * chunks_per_tile_full);
+      const int tile = tile_of(it);
+      if (tile >= num_tiles) return false;
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      row0 = m_tile * 2 * kBM + rank * kBM;
+      col0 = n_tile * kBN + c * 32;
+      return true;
+    };
+    auto request = [&](long long g) {  // leader thread: TMA-load the residual box of chunk g
+      int row0, col0;
+      if (!chunk_coords(g, row0, col0)) return;
+      const int b = static_cast<int>(g % kRing);
+      mbar_expect_tx(&rfull_bar[b], kRBoxBytes);
+      tma_load_2d(ring + b * kRBoxBytes, &tmR, &rfull_bar[b], col0, row0);
+    };
+    if (leader_thread) {
+      for (int g = 0; g < kAhead; ++g) request(g);
+    }
+    long long g = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int row = m_tile * 2 * kBM + rank * kBM + r_in_cta;
+      const float* gate_row = nullptr;
+      if (kGate) {
+        const int rclamp = row < p.M ? row : p.M - 1;
+        const int sample = rclamp / p.rows_per_sample;
+        const int r_in = rclamp - sample * p.rows_per_sample;
+        gate_row = p.gate + sample * p.gate_sample_stride + r_in * p.gate_row_stride;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c, ++g) {
+        const int col0 = n_tile * kBN + c * 32;
+        const int b = static_cast<int>(g % kRing);
+        uint8_t* box = ring + b * kRBoxBytes;
+        if (leader_thread) {
+          // box (g + kAhead) % kRing was last used by chunk g + kAhead - kRing = g - 2: its store
+          // must have finished READING shared memory; stores are committed one group per chunk
+          bulk_wait_group_read<kRing - kAhead - 1>();
+          request(g + kAhead);
+        }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN + c * 32, v);
+        // bias and gate for these 32 columns (same for every row of a sample: L1 broadcast)
+        float bsv[32], gtv[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (p.bias != nullptr && col0 + j < p.N) {
+            const uint4 bw = *reinterpret_cast<const uint4*>(p.bias + col0 + j);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bw);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __bfloat1622float2(b2[q]);
+              bsv[j + 2 * q] = f.x;
+              bsv[j + 2 * q + 1] = f.y;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) bsv[j + q] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 gq = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (kGate && col0 + j < p.N) gq = *reinterpret_cast<const float4*>(gate_row + col0 + j);
+          gtv[j] = gq.x; gtv[j + 1] = gq.y; gtv[j + 2] = gq.z; gtv[j + 3] = gq.w;
+        }
+        mbar_wait(&rfull_bar[b], static_cast<uint32_t>((g / kRing) & 1));
+        tmem_wait_ld();
+        const uint32_t row_addr = smem_u32(box) + r_in_cta * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = row_addr + ((j ^ (r_in_cta & 7)) << 4);
+          float x0, x1, x2, x3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                       : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3)
+                       : "r"(a)
+                       : "memory");
+          x0 += bf16_round(__uint_as_float(v[4 * j]) + bsv[4 * j]) * gtv[4 * j];
+          x1 += bf16_round(__uint_as_float(v[4 * j + 1]) + bsv[4 * j + 1]) * gtv[4 * j + 1];
+          x2 += bf16_round(__uint_as_float(v[4 * j + 2]) + bsv[4 * j + 2]) * gtv[4 * j + 2];
+          x3 += bf16_round(__uint_as_float(v[4 * j + 3]) + bsv[4 * j + 3]) * gtv[4 * j + 3];
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "f"(x0), "f"(x1), "f"(x2),
+                       "f"(x3)
+                       : "memory");
+        }
+        fence_proxy_async_smem();      // generic-proxy writes visible to the TMA store
+        named_bar_sync(1, 128);        // all four epilogue warps have written their rows
+        if (leader_thread) {
+          int row0, cc0;
+          chunk_coords(g, row0, cc0);
+          if (cc0 < p.N) tma_store_2d(&tmO, box, cc0, row0);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tempty0 + acc * 8);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (leader_thread) bulk_wait_group<0>();  // all stores complete before the CTA exits
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
 }  // namespace ovb
 
 extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
@@ -401,6 +659,34 @@ extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
   const int pairs = sms / 2;
   const int grid = 2 * (num_tiles < pairs ? num_tiles : pairs);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool resid_tma = needs_resid && n_split == 1 && a->ldo % 4 == 0 &&
+                         reinterpret_cast<uintptr_t>(a->resid) % 16 == 0 &&
+                         (a->epilogue == OVB_EPI_RESID_F32 || a->gate_row_stride == 0) &&
+                         getenv("OVB_GEMM_NO_TMA_EPILOGUE") == nullptr;
+  if (resid_tma) {
+    CUtensorMap tmR, tmO;
+    const uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->M)};
+    const uint32_t box[2] = {32, kBM};
+    const uint64_t rs[1] = {static_cast<uint64_t>(a->ldr) * 4};
+    const uint64_t os[1] = {static_cast<uint64_t>(a->ldo) * 4};
+    int rc = encode_tmap_f32(&tmR, a->resid, 2, dims, rs, box);
+    if (rc != OVB_OK) return rc;
+    rc = encode_tmap_f32(&tmO, a->out, 2, dims, os, box);
+    if (rc != OVB_OK) return rc;
+    static bool attr2 = false;
+    if (!attr2) {
+      OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_resid_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmResidSmem));
+      OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_resid_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmResidSmem));
+      attr2 = true;
+    }
+    if (a->epilogue == OVB_EPI_GATE_RESID_F32)
+      gemm_resid_tma_kernel<true><<<grid, kGemmThreads, kGemmResidSmem, st>>>(tmA, tmB, tmR, tmO, p);
+    else
+      gemm_resid_tma_kernel<false><<<grid, kGemmThreads, kGemmResidSmem, st>>>(tmA, tmB, tmR, tmO, p);
+    OVB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return OVB_OK;
+  }
   switch (a->epilogue) {
     case OVB_EPI_BF16: gemm_bf16_kernel<OVB_EPI_BF16><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
     case OVB_EPI_GELU_BF16: gemm_bf16_kernel<OVB_EPI_GELU_BF16><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;

@@ -87,6 +87,45 @@ int encode_tmap_bf16_ex(CUtensorMap* out, const void* gptr, int rank, const uint
   return OVB_OK;
 }
 
+int encode_tmap_f32(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled not available from the CUDA driver");
+    return OVB_ERR_CUDA;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstrides[i] = strides_bytes[i];
+    if (gstrides[i] % 16 != 0) {
+      set_last_error("TMA stride %d = %llu bytes is not a multiple of 16", i,
+                     static_cast<unsigned long long>(gstrides[i]));
+      return OVB_ERR_INVALID_ARGUMENT;
+    }
+  }
+  if (box[0] * 4 > 128) {
+    set_last_error("TMA inner box of %u fp32 exceeds the 128-byte swizzle span", box[0]);
+    return OVB_ERR_INVALID_ARGUMENT;
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank),
+                  const_cast<void*>(gptr), gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(fp32) failed with CUresult %d", static_cast<int>(r));
+    return OVB_ERR_CUDA;
+  }
+  return OVB_OK;
+}
+
 int device_sm_count() {
   static int sms[64] = {0};
   int dev = 0;

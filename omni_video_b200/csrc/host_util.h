@@ -41,6 +41,10 @@ int encode_tmap_bf16_ex(CUtensorMap* out, const void* gptr, int rank, const uint
                         const uint64_t* strides_bytes, const uint32_t* box,
                         const uint32_t* elem_strides, int swizzle_bytes);
 
+// fp32 tiled tensor map (128-byte swizzle: inner box <= 32 floats), zero fill / clipping out of bounds.
+int encode_tmap_f32(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box);
+
 int device_sm_count();
 void count_launch();
 
