@@ -269,10 +269,13 @@ def run_ours(args):
 
     # ---------------- device-resident run (value) ----------------
     latent = latent0.clone()
+    # the sampler starts before the warm-up steps (nvidia-smi needs ~0.3 s to produce its first
+    # line, longer than a multi-GPU timed region); only samples drawing >= half of the peak power
+    # seen, i.e. taken under load, enter the median
+    clocks = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         latent = stepper.step(latent, ctx_c, ctx_u, i)
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     ops.timeline = []
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
