@@ -359,7 +359,17 @@ extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
     if (rc != OVB_OK) return rc;
   }
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(a->H) * 128, static_cast<uint64_t>(a->Lk),
+    // The K/V maps end at the longest valid key length: rows past it are never fetched (TMA zero
+    // fill), as in the reference, which trims k/v to k_lens before calling flash-attn
+    // (attention.py:75-77).  (Inside a ragged batch, masked rows of shorter samples are still read
+    // and multiplied by P = 0, so they must hold finite values.)
+    int max_kl = 1;
+    for (int b = 0; b < a->B; ++b) {
+      const int kl = a->k_lens != nullptr ? a->k_lens[b] : a->Lk;
+      if (kl > max_kl) max_kl = kl;
+    }
+    if (max_kl > a->Lk) max_kl = a->Lk;
+    const uint64_t dims[3] = {static_cast<uint64_t>(a->H) * 128, static_cast<uint64_t>(max_kl),
                               static_cast<uint64_t>(a->B)};
     const uint64_t ks[2] = {static_cast<uint64_t>(a->k_row_stride) * 2,
                             static_cast<uint64_t>(a->B > 1 ? a->k_batch_stride

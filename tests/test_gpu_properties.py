@@ -1,0 +1,139 @@
+"""Size-independent properties at BASELINE.json's full sizes (32760 tokens, 81-frame clips), where the
+CPU oracle would take minutes: softmax rows sum to one, key-permutation invariance, key-length
+masking, sampled-row checks of the GEMM epilogues against fp32 matmul, causality of the VAE in time,
+determinism."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+L_FULL = 32760  # 81x480x832 video -> 21x30x52 patch grid
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from omni_video_b200 import ops as o
+    return o
+
+
+def test_attention_full_length_rows_sum_to_one_and_mask(ops):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    H = 2
+    q = torch.randn(1, L_FULL, H, 128, generator=g, device="cuda").to(bf16)
+    k = torch.randn(1, L_FULL, H, 128, generator=g, device="cuda").to(bf16)
+    const = torch.linspace(-2, 2, 128, device="cuda").to(bf16)
+    v = const.expand(1, L_FULL, H, 128).contiguous()
+    out = ops.attention(q, k, v)
+    # sum_j p_ij = 1  =>  out_i = const, up to the bf16 rounding of P and of the output
+    assert (out.float() - const.float()).abs().max().item() <= 2 ** -6
+    # keys >= k_len must not matter, whatever they hold
+    kl = L_FULL - 1000
+    k2, v2 = k.clone(), torch.randn_like(v)
+    ref = ops.attention(q, k2, v2, k_lens=[kl])
+    k2[:, kl:] = 50.0
+    v2[:, kl:] = float("nan")
+    got = ops.attention(q, k2, v2, k_lens=[kl])
+    assert torch.equal(got, ref)
+
+
+def test_attention_key_permutation_invariance(ops):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    L, H = 8192, 3
+    q, k, v = (torch.randn(1, L, H, 128, generator=g, device="cuda").to(bf16) for _ in range(3))
+    perm = torch.randperm(L, generator=g, device="cuda")
+    a = ops.attention(q, k, v)
+    b = ops.attention(q, k[:, perm].contiguous(), v[:, perm].contiguous())
+    assert (a.float() - b.float()).abs().max().item() <= 2e-2
+    assert ((a.float() - b.float()).norm() / a.float().norm()).item() <= 5e-3
+
+
+@pytest.mark.parametrize("N,K", [(1536, 1536), (4608, 1536), (1536, 8960)])
+def test_gemm_full_length_sampled_rows(ops, N, K):
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    M = 2 * L_FULL  # the CFG-batched forward
+    a = torch.randn(M, K, generator=g, device="cuda").to(bf16)
+    w = (torch.randn(N, K, generator=g, device="cuda") / K ** 0.5).to(bf16)
+    b = torch.randn(N, generator=g, device="cuda").to(bf16)
+    rows = torch.cat([torch.randint(0, M, (96,), generator=g, device="cuda"),
+                      torch.tensor([0, 127, 128, 255, 256, L_FULL - 1, L_FULL, M - 1], device="cuda")])
+    ref = a[rows].float() @ w.float().T + b.float()
+    out = ops.gemm(a, w, b)
+    assert (out[rows].float() - ref.to(bf16).float()).abs().max().item() <= ref.abs().max().item() * 2 ** -7
+    # gated fp32 residual, in place, per-sample gate (the O-projection / FFN2 form)
+    x = torch.randn(M, N, generator=g, device="cuda")
+    gate = torch.randn(2, N, generator=g, device="cuda")
+    x0 = x[rows].clone()
+    ops.gemm(a, w, b, epilogue=ops.EPI_GATE_RESID_F32, out=x, resid=x, gate=gate, rows_per_sample=L_FULL)
+    want = x0 + ref.to(bf16).float() * gate[(rows >= L_FULL).long()]
+    assert (x[rows] - want).abs().max().item() <= 2 ** -6 * max(1.0, want.abs().max().item())
+    assert bool(torch.isfinite(x).all())
+
+
+def _vae():
+    from omni_video_b200.modules.vae2_1 import Wan2_1_VAE
+    vae = Wan2_1_VAE(vae_pth=None, device="cuda")
+    vae.model.load_state_dict(synth.vae_state_dict(seed=1818), strict=True)
+    return vae
+
+
+def test_vae_decode_is_causal_in_time_and_deterministic():
+    """Output frame f depends only on latent frames <= ceil(f/4) (CausalConv3d pads on the left,
+    reference vae2_1.py:16-35): changing the LAST latent frame must leave the first 1+4(T-2)
+    video frames bit-identical."""
+    vae = _vae()
+    z = synth.vae_latent((4, 8, 12), seed=11).cuda()
+    a = vae.decode([z])[0]
+    assert torch.equal(a, vae.decode([z])[0])
+    z2 = z.clone()
+    z2[:, -1] += 1.0
+    b = vae.decode([z2])[0]
+    keep = 1 + 4 * (z.shape[1] - 2)
+    assert torch.equal(a[:, :keep], b[:, :keep])
+    assert not torch.equal(a[:, keep:], b[:, keep:])
+
+
+def test_vae_encode_is_causal_in_time():
+    vae = _vae()
+    v = synth.vae_video((13, 32, 48), seed=5).cuda()
+    a = vae.encode([v])[0]                       # [16, 4, 4, 6]
+    v2 = v.clone()
+    v2[:, -4:] = -v2[:, -4:]
+    b = vae.encode([v2])[0]
+    assert torch.equal(a[:, :-1], b[:, :-1])
+    assert not torch.equal(a[:, -1], b[:, -1])
+
+
+def test_vae_decode_mid_size_vs_oracle():
+    """A clip larger than the goldens (latent 3x12x20 -> 9x96x160) against the fp32 oracle."""
+    from oracle import vae as V
+    sd = synth.vae_state_dict(seed=1818)
+    z = synth.vae_latent((3, 12, 20), seed=3)
+    out = _vae().decode([z.cuda()])[0].cpu()
+    ref = V.vae_decode(sd, z)
+    assert V.psnr(out, ref) >= 40.0
+
+
+def test_dit_block_full_length_batch_consistency():
+    """One 1.3B-width block at the full token count: the CFG-batched forward (B=2) gives, sample by
+    sample, exactly what two B=1 forwards give, and is deterministic."""
+    from omni_video_b200.modules.model import WanModel
+    cfg = dict(synth.DIT_1_3B, num_layers=1, text_dim=256)
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        m = WanModel(**cfg)
+    torch.nn.init.normal_(m.head.head.weight, std=0.02)
+    m = m.to(bf16).eval().requires_grad_(False)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(16, 21, 60, 104, generator=g, device="cuda")
+    c1 = torch.randn(77, 256, generator=g, device="cuda").to(bf16)
+    c2 = torch.randn(33, 256, generator=g, device="cuda").to(bf16)
+    t = torch.tensor([999, 999], device="cuda")
+    both = m([x, x], t=t, context=[c1, c2], seq_len=L_FULL)
+    one = m([x], t=t[:1], context=[c1], seq_len=L_FULL)[0]
+    two = m([x], t=t[:1], context=[c2], seq_len=L_FULL)[0]
+    assert torch.equal(both[0], one) and torch.equal(both[1], two)
+    assert bool(torch.isfinite(both[0]).all()) and both[0].shape == (16, 21, 60, 104)
+    assert not torch.equal(both[0], both[1])
