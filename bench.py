@@ -319,13 +319,18 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3))
 
+    # ---------------- VAE decode of the sampled latent (all ranks: H-strips with halo exchange) ---
+    peaks = load_peaks()
+    vae = None
+    if not args.no_vae:
+        vae = vae_decode_leg((Fr, H, W), dev, peaks, dist.group.WORLD if world > 1 else None, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---------------- roofline of the dominant kernel ----------------
-    peaks = load_peaks()
     torch.cuda.synchronize()
     agg = {}
     for kind, flops, shape, s, e in timeline:
@@ -360,10 +365,6 @@ def run_ours(args):
                                     frac=round(whole_tf / world / peaks["tflops"], 4),
                                     tflop_per_step=round(2.0 * fl["total"] / 1e12, 1)))
 
-    vae = None
-    if not args.no_vae:
-        vae = vae_decode_leg((Fr, H, W), dev, peaks)
-
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_leg(cfg, (Fr, H, W), args.text_len, budget_s=args.cpu_budget)
@@ -391,10 +392,11 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def vae_decode_leg(grid_lat, dev, peaks):
-    """BASELINE.json configs[1] ends with one Wan2.1 VAE decode of the sampled latent (rank 0, as in
-    x2x_gen_unified.py:512-524).  Reported beside the step rate, not folded into it: one decode per
-    50 steps.  Algorithmic FLOPs: SURVEY.md Appendix A cost model (measured on the reference with
+def vae_decode_leg(grid_lat, dev, peaks, group=None, world=1):
+    """BASELINE.json configs[1] ends with one Wan2.1 VAE decode of the sampled latent (the reference
+    decodes on rank 0 only, x2x_gen_unified.py:512-524; with N > 1 we split the clip into H-strips
+    over all ranks, halo rows exchanged before every spatial conv).  Reported beside the step rate,
+    not folded into it: one decode per 50 steps.  Algorithmic FLOPs: SURVEY.md Appendix A cost model (measured on the reference with
     FlopCounterMode): 0.688 GFLOP per latent pixel for frame 0 + 2.162 per later frame, plus the
     per-frame single-head attention."""
     import torch
@@ -408,24 +410,36 @@ def vae_decode_leg(grid_lat, dev, peaks):
         if p.dim() > 1 and "gamma" not in name:
             p.data.copy_(torch.randn(p.shape, generator=g, device="cuda") / p[0].numel() ** 0.5)
     z = torch.randn((16, T, h, w), generator=g, device=dev)
+    if group is not None:
+        vae.set_strip_group(group)
     flops = (0.688e9 + 2.162e9 * (T - 1)) * h * w + 4.0 * (h * w) ** 2 * 384 * T
     times = []
     for it in range(3):
         ops.timeline = [] if it == 2 else None
+        if group is not None:
+            import torch.distributed as dist
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = vae.decode([z])[0]
         e1.record()
         torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
+        ms_it = e0.elapsed_time(e1)
+        if group is not None:
+            tt = torch.tensor([ms_it], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_it = float(tt.item())
+        times.append(ms_it)
     tl, ops.timeline = ops.timeline, None
     conv_fl = sum(t[1] for t in tl if t[0] == "conv")
     conv_ms = sum(t[3].elapsed_time(t[4]) for t in tl if t[0] == "conv")
     norm_b = sum(t[1] for t in tl if t[0] == "norm")
     norm_ms = sum(t[3].elapsed_time(t[4]) for t in tl if t[0] == "norm")
     ms = min(times[1:])
-    res = dict(ms=round(ms, 1), out_shape=list(out.shape), tflops=round(flops / ms / 1e9, 1),
-               frac_of_bf16_peak=round(flops / ms / 1e9 / peaks["tflops"], 4),
+    res = dict(ms=round(ms, 1), out_shape=list(out.shape), n_gpus=world,
+               layout="single GPU" if world == 1 else f"{world} H-strips, halo exchange per spatial conv",
+               tflops=round(flops / ms / 1e9, 1),
+               frac_of_bf16_peak=round(flops / ms / 1e9 / peaks["tflops"] / world, 4),
                conv_kernel=dict(tflops=round(conv_fl / max(conv_ms, 1e-9) / 1e9, 1), share=round(conv_ms / ms, 3)),
                norm_kernel=dict(gbs=round(norm_b / max(norm_ms, 1e-9) / 1e6, 1), share=round(norm_ms / ms, 3),
                                 frac_of_hbm_peak=round(norm_b / max(norm_ms, 1e-9) / 1e6 / peaks["hbm"], 4)),

@@ -231,6 +231,11 @@ class Wan2_1_VAE:
     def _engine(self) -> "VAEEngine":
         return self.model.engine(self.scale)
 
+    def set_strip_group(self, group):
+        """Multi-GPU: every rank of `group` calls encode/decode with the SAME full input and gets
+        the full output; the work is split into H-strips with halo exchange (None: single GPU)."""
+        self._engine().set_strip_group(group)
+
     def encode(self, videos):
         """videos: list of [3, T, H, W] -> list of fp32 [16, T', H/8, W/8]."""
         return self._engine().encode(videos)
@@ -238,6 +243,69 @@ class Wan2_1_VAE:
     def decode(self, zs):
         """zs: list of [16, T, h, w] -> list of fp32 [3, 1+4(T-1), 8h, 8w] clamped to [-1, 1]."""
         return self._engine().decode(zs, clamp=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# Spatial strips across GPUs (SURVEY.md §8(e)): rank r of p owns latent rows [h0, h1) of every
+# activation (x 2^k at finer levels).  Per-voxel work is strip-local; a convolution with a spatial
+# extent needs one row of halo from each neighbour at ITS input resolution, exchanged with NCCL
+# point-to-point calls right before the conv; the single-head attention of the middle block gathers
+# the (latent-resolution) rows of all strips.  The reference decodes on one rank only
+# (x2x_gen_unified.py:512-524); this is the multi-GPU layout of BASELINE.json configs[4].
+# ------------------------------------------------------------------------------------------------
+class Strip:
+    def __init__(self, group):
+        import torch.distributed as dist
+        self.group = group
+        self.p = dist.get_world_size(group)
+        self.r = dist.get_rank(group)
+        self.ranks = dist.get_process_group_ranks(group)
+
+    def rows(self, H: int, r: Optional[int] = None):
+        """[h0, h1) of rank r when H latent rows are cut into p nearly equal strips."""
+        r = self.r if r is None else r
+        return (r * H) // self.p, ((r + 1) * H) // self.p
+
+
+def halo_exchange(x: torch.Tensor, strip: Strip, top: bool, bottom: bool) -> torch.Tensor:
+    """x: this rank's rows [T, Hl, W, C].  Returns x with one halo row from the upper neighbour
+    prepended (if `top`) and one from the lower neighbour appended (if `bottom`); zeros at the
+    image border, which is exactly the convolution's zero padding there."""
+    import torch.distributed as dist
+    r, p = strip.r, strip.p
+    t_halo = torch.zeros_like(x[:, :1])
+    b_halo = torch.zeros_like(x[:, :1])
+    ops_ = []
+    # my first row is the upper neighbour's bottom halo; my last row the lower neighbour's top halo
+    if r > 0:
+        if bottom:
+            ops_.append(dist.P2POp(dist.isend, x[:, :1].contiguous(), strip.ranks[r - 1], group=strip.group))
+        if top:
+            ops_.append(dist.P2POp(dist.irecv, t_halo, strip.ranks[r - 1], group=strip.group))
+    if r < p - 1:
+        if top:
+            ops_.append(dist.P2POp(dist.isend, x[:, -1:].contiguous(), strip.ranks[r + 1], group=strip.group))
+        if bottom:
+            ops_.append(dist.P2POp(dist.irecv, b_halo, strip.ranks[r + 1], group=strip.group))
+    if ops_:
+        for req in dist.batch_isend_irecv(ops_):
+            req.wait()
+    parts = ([t_halo] if top else []) + [x] + ([b_halo] if bottom else [])
+    return torch.cat(parts, dim=1)
+
+
+def gather_rows(x: torch.Tensor, strip: Strip, dim: int, sizes: List[int]) -> torch.Tensor:
+    """All-gather strips of unequal height along `dim` (padded to the tallest strip for NCCL)."""
+    import torch.distributed as dist
+    hmax = max(sizes)
+    xm = x.movedim(dim, 0).contiguous()
+    if xm.shape[0] < hmax:
+        pad = torch.zeros((hmax - xm.shape[0],) + tuple(xm.shape[1:]), device=x.device, dtype=x.dtype)
+        xm = torch.cat([xm, pad], dim=0)
+    full = torch.empty((strip.p * hmax,) + tuple(xm.shape[1:]), device=x.device, dtype=x.dtype)
+    dist.all_gather_into_tensor(full, xm, group=strip.group)   # concatenated form (gloo and NCCL)
+    out = torch.cat([full[i * hmax:i * hmax + n] for i, n in enumerate(sizes)], dim=0)
+    return out.movedim(0, dim).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -251,6 +319,14 @@ class VAEEngine:
         self.mean_host, self.std_host = mean.detach().float().cpu(), std.detach().float().cpu()
         self._packed: Dict[str, object] = {}
         self._key = None
+        self.strip: Optional[Strip] = None   # set_strip_group()
+        self._lat_H = None                   # latent rows of the clip being processed (strip mode)
+
+    def set_strip_group(self, group):
+        """Run encode/decode as H-strips over the ranks of `group` (None: single GPU)."""
+        self.strip = None if group is None else Strip(group)
+        if self.strip is not None and self.strip.p == 1:
+            self.strip = None
 
     # -------------------------------------------------------------------------------- weights
     def _params(self) -> Dict[str, torch.Tensor]:
@@ -291,9 +367,19 @@ class VAEEngine:
         return self._packed[key]
 
     # -------------------------------------------------------------------------------- blocks
+    def _halo(self, x, pc):
+        """Strip mode: add the halo rows `pc` reads.  Returns (input tensor, row shift of the taps)."""
+        lo, hi = pc.spatial_rows
+        if self.strip is None or (lo == 0 and hi == 0):
+            return x, 0
+        top, bottom = lo < 0, hi > 0
+        return halo_exchange(x, self.strip, top, bottom), (1 if top else 0)
+
     def _causal_conv(self, x, name, resid=None):
         T, H, W, _ = x.shape
-        return vae_ops.conv3d(x, self._conv(name), (T, H, W), resid=resid)
+        pc = self._conv(name)
+        xin, shift = self._halo(x, pc)
+        return vae_ops.conv3d(xin, pc, (T, H, W), resid=resid, dh_shift=shift)
 
     def _residual_block(self, x, p):
         sd = self._params()
@@ -307,7 +393,7 @@ class VAEEngine:
     def _attention_block(self, x, p):
         T, H, W, Cc = x.shape
         hw = H * W
-        if hw % 8 != 0:
+        if hw % 8 != 0 and self.strip is None:
             raise NotImplementedError(f"VAE attention needs h*w % 8 == 0 (got {H}x{W})")
         x2 = x.view(T * hw, Cc)
         xn = vae_ops.rmsnorm_silu(x2, self._gamma(p + "norm.gamma"), silu=False)
@@ -315,17 +401,31 @@ class VAEEngine:
         bias = sd[p + "to_qkv.bias"].detach().to(bf16)
         wqk = self._mat(p + "to_qkv.weight", slice(0, 2 * Cc))
         wv = self._mat(p + "to_qkv.weight", slice(2 * Cc, 3 * Cc))
-        qk = ops.gemm(xn, wqk, bias[:2 * Cc].contiguous(), epilogue=EPI_BF16)   # [T*hw, 2C]
+        # queries: this rank's rows; keys/values: every row of the frame (strip mode gathers the
+        # normalised latent-resolution rows of all ranks; K and V^T are then computed replicated)
+        if self.strip is not None:
+            sizes = [self.strip.rows(self._lat_H, r)[1] - self.strip.rows(self._lat_H, r)[0]
+                     for r in range(self.strip.p)]
+            xk = gather_rows(xn.view(T, H, W, Cc), self.strip, 1, sizes)        # [T, H_all, W, C]
+            hk = xk.shape[1] * W
+            if hk % 8 != 0:
+                raise NotImplementedError(f"VAE attention needs h*w % 8 == 0 (got {xk.shape[1]}x{W})")
+            xk = xk.view(T * hk, Cc)
+        else:
+            xk, hk = xn, hw
+        q = ops.gemm(xn, wqk[:Cc], bias[:Cc].contiguous(), epilogue=EPI_BF16)           # [T*hw, C]
+        k = ops.gemm(xk, wqk[Cc:], bias[Cc:2 * Cc].contiguous(), epilogue=EPI_BF16)     # [T*hk, C]
         o = torch.empty((T * hw, Cc), device=x.device, dtype=bf16)
-        S = torch.empty((hw, hw), device=x.device, dtype=f32)
-        P = torch.empty((hw, hw), device=x.device, dtype=bf16)
-        vt = torch.empty((Cc, hw), device=x.device, dtype=bf16)
+        S = torch.empty((hw, hk), device=x.device, dtype=f32)
+        P = torch.empty((hw, hk), device=x.device, dtype=bf16)
+        vt = torch.empty((Cc, hk), device=x.device, dtype=bf16)
         bv = bias[2 * Cc:].contiguous()
         scale = 1.0 / math.sqrt(Cc)
         for f in range(T):
             rows = slice(f * hw, (f + 1) * hw)
-            ops.gemm(wv, xn[rows], None, epilogue=EPI_BF16, out=vt)              # V^T = Wv Xn^T   [C, hw]
-            ops.gemm(qk[rows, :Cc], qk[rows, Cc:], None, epilogue=EPI_F32, out=S)  # Q K^T        [hw, hw]
+            krows = slice(f * hk, (f + 1) * hk)
+            ops.gemm(wv, xk[krows], None, epilogue=EPI_BF16, out=vt)             # V^T = Wv Xn^T   [C, hk]
+            ops.gemm(q[rows], k[krows], None, epilogue=EPI_F32, out=S)            # Q K^T          [hw, hk]
             vae_ops.softmax_rows(S, scale, out=P)
             ops.gemm(P, vt, bv, epilogue=EPI_BF16, out=o[rows])                   # P V + b_v (rows of P sum to 1)
         wp = self._mat(p + "proj.weight")
@@ -352,15 +452,21 @@ class VAEEngine:
         phases = self._packed[key]
         Co = Cc // 2
         out = torch.empty((T, 2 * H, 2 * W, Co), device=x.device, dtype=bf16)
+        # strip mode: one halo exchange (both neighbours) serves the four phases
+        xin, shift = (x, 0) if self.strip is None else (halo_exchange(x, self.strip, True, True), 1)
         for (a, b), pc in phases.items():
-            vae_ops.conv3d(x, pc, (T, H, W), out=out, out_strides=(4 * H * W * Co, 4 * W * Co, 2 * Co),
-                           out_base=(a * 2 * W + b) * Co)
+            vae_ops.conv3d(xin, pc, (T, H, W), out=out, out_strides=(4 * H * W * Co, 4 * W * Co, 2 * Co),
+                           out_base=(a * 2 * W + b) * Co, dh_shift=shift)
         return out
 
     def _downsample(self, x, p, three_d: bool):
         T, H, W, Cc = x.shape
         Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1                     # ZeroPad2d(0,1,0,1) + k3 s2
         pc = self._conv(p + "resample.1", stride=(1, 2, 2), spatial_pad=(0, 0))
+        if self.strip is not None:
+            assert H % 2 == 0, "strip heights must be even at every stride-2 level"
+            Ho = H // 2
+            x = halo_exchange(x, self.strip, False, True)    # rows 2h, 2h+1, 2h+2: one row from below
         x = vae_ops.conv3d(x, pc, (T, Ho, Wo))
         if three_d and T > 1:
             # out[0] = x[0]; out[j] = time_conv(x[2j-2], x[2j-1], x[2j])  (stride 2, no padding)
@@ -400,6 +506,11 @@ class VAEEngine:
             zc = z.shape[0]
             x = vae_ops.planar_to_cl(z, self.std, self.mean, 16)                 # z*std + mean (:546-550)
             assert zc == 16, "Wan2.1 VAE has z_dim 16"
+            if self.strip is not None:
+                self._lat_H = x.shape[1]
+                h0, h1 = self.strip.rows(self._lat_H)
+                assert h1 > h0, "more strips than latent rows"
+                x = x[:, h0:h1].contiguous()
             T, H, W, _ = x.shape
             x = vae_ops.conv3d(x, self._conv("conv2"), (T, H, W))                # 1x1x1 (:552)
             x = self._causal_conv(x, "decoder.conv1")
@@ -408,9 +519,16 @@ class VAEEngine:
             vae_ops.rmsnorm_silu(x, self._gamma("decoder.head.0.gamma"), out=x)
             T, H, W, _ = x.shape
             out = torch.empty((3, T, H, W), device=self.dev, dtype=f32)
-            vae_ops.conv3d(x, self._conv("decoder.head.2"), (T, H, W), out=out, out_strides=(H * W, W, 1),
+            pc_head = self._conv("decoder.head.2")
+            x, hshift = self._halo(x, pc_head)
+            vae_ops.conv3d(x, pc_head, (T, H, W), out=out, out_strides=(H * W, W, 1), dh_shift=hshift,
                            out_mode=CONV_OUT_F32_PLANAR_CLAMP if clamp else vae_ops.CONV_OUT_F32_PLANAR,
                            plane_stride=T * H * W)
+            if self.strip is not None:  # every rank ends up with the whole clip
+                scale_h = H // (self.strip.rows(self._lat_H)[1] - self.strip.rows(self._lat_H)[0])
+                sizes = [(self.strip.rows(self._lat_H, r)[1] - self.strip.rows(self._lat_H, r)[0]) * scale_h
+                         for r in range(self.strip.p)]
+                out = gather_rows(out, self.strip, 2, sizes)
             outs.append(out)
         return outs
 
@@ -421,6 +539,12 @@ class VAEEngine:
         for v in videos:
             v = v.to(self.dev, dtype=f32).contiguous()
             assert v.shape[0] == 3 and (v.shape[1] - 1) % 4 == 0, "video must be [3, 1+4k, H, W]"
+            if self.strip is not None:
+                assert v.shape[2] % 8 == 0
+                self._lat_H = v.shape[2] // 8
+                h0, h1 = self.strip.rows(self._lat_H)
+                assert h1 > h0, "more strips than latent rows"
+                v = v[:, :, 8 * h0:8 * h1].contiguous()
             x = vae_ops.planar_to_cl(v, self._ones[3], self._zeros[3], 16)
             x = self._causal_conv(x, "encoder.conv1")
             x = self._stack(x, "encoder.downsamples.", up=False)
@@ -431,5 +555,10 @@ class VAEEngine:
             x = vae_ops.conv3d(x, self._conv("conv1"), (T, H, W))                # 1x1x1 (:534)
             z = self.mean.numel()
             inv = 1.0 / self.std
-            outs.append(vae_ops.cl_to_planar(x, inv, -self.mean * inv, z))        # (mu - mean)/std (:535-539)
+            mu = vae_ops.cl_to_planar(x, inv, -self.mean * inv, z)                # (mu - mean)/std (:535-539)
+            if self.strip is not None:
+                sizes = [self.strip.rows(self._lat_H, r)[1] - self.strip.rows(self._lat_H, r)[0]
+                         for r in range(self.strip.p)]
+                mu = gather_rows(mu, self.strip, 2, sizes)
+            outs.append(mu)
         return outs

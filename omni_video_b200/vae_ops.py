@@ -31,9 +31,21 @@ class PackedConv:
         self.cin, self.cout, self.stride = cin, cout, tuple(stride)
         n = len(taps)
         self.n_taps = n
+        self.taps = [tuple(t) for t in taps]
         self._dt = (C.c_int8 * n)(*[t[0] for t in taps])
         self._dh = (C.c_int8 * n)(*[t[1] for t in taps])
         self._dw = (C.c_int8 * n)(*[t[2] for t in taps])
+        self._dh_shifted = {0: self._dh}
+
+    @property
+    def spatial_rows(self):
+        """(lowest, highest) input-row offset any tap reads: which halo rows a strip needs."""
+        return min(t[1] for t in self.taps), max(t[1] for t in self.taps)
+
+    def dh_array(self, shift: int):
+        if shift not in self._dh_shifted:
+            self._dh_shifted[shift] = (C.c_int8 * self.n_taps)(*[t[1] + shift for t in self.taps])
+        return self._dh_shifted[shift]
 
 
 def _pad_rows(w2: torch.Tensor) -> torch.Tensor:
@@ -93,8 +105,10 @@ def conv3d(x: torch.Tensor, pc: PackedConv, out_extent: Tuple[int, int, int], *,
            out: Optional[torch.Tensor] = None, out_strides: Optional[Tuple[int, int, int]] = None,
            out_base: int = 0, n_group: int = 0, group_stride: int = 0,
            resid: Optional[torch.Tensor] = None, out_mode: int = CONV_OUT_BF16,
-           plane_stride: int = 0) -> torch.Tensor:
-    """x: bf16 [Ti, Hi, Wi, Cin] contiguous.  Default output: a new bf16 [To, Ho, Wo, Cout]."""
+           plane_stride: int = 0, dh_shift: int = 0) -> torch.Tensor:
+    """x: bf16 [Ti, Hi, Wi, Cin] contiguous.  Default output: a new bf16 [To, Ho, Wo, Cout].
+    dh_shift is added to every tap's row offset (a strip whose input carries `dh_shift` halo rows
+    on top)."""
     _need_cuda(x, pc.w, out, resid)
     lib = _lib.load()
     assert x.dtype == bf16 and x.dim() == 4 and x.is_contiguous(), "x must be contiguous bf16 [T,H,W,C]"
@@ -112,7 +126,7 @@ def conv3d(x: torch.Tensor, pc: PackedConv, out_extent: Tuple[int, int, int], *,
     a.bias = None if pc.bias is None else pc.bias.data_ptr()
     a.Cout, a.n_taps = pc.cout, pc.n_taps
     a.tap_dt = C.cast(pc._dt, C.POINTER(C.c_int8))
-    a.tap_dh = C.cast(pc._dh, C.POINTER(C.c_int8))
+    a.tap_dh = C.cast(pc.dh_array(dh_shift), C.POINTER(C.c_int8))
     a.tap_dw = C.cast(pc._dw, C.POINTER(C.c_int8))
     a.st, a.sh, a.sw = pc.stride
     a.To, a.Ho, a.Wo = To, Ho, Wo

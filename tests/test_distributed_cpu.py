@@ -103,3 +103,41 @@ def test_ulysses_host_logic_two_ranks_gloo():
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}
+
+
+def _strip_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from omni_video_b200.modules.vae2_1 import Strip, gather_rows, halo_exchange
+        strip = Strip(dist.new_group(list(range(world))))
+        H = 7                                        # uneven strips: 3 + 4 rows
+        full = torch.arange(2 * H * 3 * 4, dtype=torch.float32).view(2, H, 3, 4)   # [T, H, W, C]
+        h0, h1 = strip.rows(H)
+        assert (h0, h1) == ((0, 3) if rank == 0 else (3, 7))
+        mine = full[:, h0:h1].contiguous()
+        ext = halo_exchange(mine, strip, True, True)
+        want = torch.cat([full[:, h0 - 1:h0] if h0 > 0 else torch.zeros_like(full[:, :1]), mine,
+                          full[:, h1:h1 + 1] if h1 < H else torch.zeros_like(full[:, :1])], dim=1)
+        assert torch.equal(ext, want)
+        only_bottom = halo_exchange(mine, strip, False, True)
+        assert torch.equal(only_bottom, want[:, 1:])
+        sizes = [strip.rows(H, r)[1] - strip.rows(H, r)[0] for r in range(world)]
+        assert torch.equal(gather_rows(mine, strip, 1, sizes), full)
+        results[rank] = "ok"
+    except Exception as ex:  # pragma: no cover
+        results[rank] = f"{type(ex).__name__}: {ex}"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_vae_strip_halo_and_gather_two_ranks_gloo():
+    """Host logic of the VAE's multi-GPU strips: halo rows come from the right neighbour, image
+    borders get zeros, uneven strips gather back in order."""
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_strip_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}

@@ -233,3 +233,18 @@ def test_vae_encode_decode_roundtrip_shapes_and_determinism():
     raw = vae.model.decode(z1.unsqueeze(0), vae.scale)
     assert raw.shape == (1, 3, 5, 32, 48)
     assert torch.equal(raw[0].clamp(-1, 1), x)
+
+
+def test_vae_strips_two_gpus_match_single_gpu():
+    """Runs scripts/vae_strip_check.py under torchrun when the box has >= 2 GPUs (host logic on CPU:
+    tests/test_distributed_cpu.py::test_vae_strip_halo_and_gather_two_ranks_gloo)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29547",
+                        os.path.join(root, "scripts", "vae_strip_check.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
