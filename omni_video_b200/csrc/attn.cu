@@ -21,6 +21,18 @@
 
 namespace ovb {
 
+#ifdef OVB_ATTN_TRACE
+// Debug build only (scripts/attn_trace.py): clock64() stamps of one CTA's pipeline events.
+__device__ long long* g_attn_trace = nullptr;
+#define OVB_TRACE(cond, slot)                                                      \
+  do {                                                                             \
+    if ((cond) && blockIdx.x == 3 && blockIdx.y == 0 && g_attn_trace != nullptr)  \
+      g_attn_trace[(slot)] = clock64();                                            \
+  } while (0)
+#else
+#define OVB_TRACE(cond, slot) do { } while (0)
+#endif
+
 constexpr int kAttnThreads = 384;
 constexpr int kTileBytes = 128 * 128 * 2;  // 32 KB : one 128x128 bf16 tile (two 64-col TMA boxes)
 constexpr int kBoxBytes = 128 * 64 * 2;    // 16 KB
@@ -161,22 +173,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ph = (j / kKVStages) & 1;
         mbar_wait(&k_full[s], ph);
         tc_fence_after();
+        OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 0);   // MMA: about to issue QK0(j)
         issue_qk(0, s);
         umma_commit(&s_full[0]);
+        OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 1);   // MMA: QK0 issued
         if (j > 0) {
           const int sp = (j - 1) % kKVStages;
           mbar_wait(&p_full[1], (j - 1) & 1);
           tc_fence_after();
+          OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 2);   // MMA: P1(j-1) seen
           issue_pv(1, sp, j - 1 == 0);
           umma_commit(&v_empty[sp]);
         }
         issue_qk(1, s);
         umma_commit(&s_full[1]);
         umma_commit(&k_empty[s]);
+        OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 3);   // MMA: QK1(j) issued
         mbar_wait(&p_full[0], j & 1);
+        OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 4);   // MMA: P0(j) seen
         mbar_wait(&v_full[s], ph);
         tc_fence_after();
         issue_pv(0, s, j == 0);
+        OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 5);   // MMA: PV0(j) issued
       }
       umma_commit(&o_full[0]);
       {
@@ -205,6 +223,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[wg], j & 1);
       tc_fence_after();
+      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 0);  // S seen
       float s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -214,20 +233,64 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int t = 0; t < 32; ++t) s[c * 32 + t] = __uint_as_float(r[t]);
       }
       tmem_wait_ld();
+      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 1);  // S loaded
       const int valid = k_len - j * 128;  // >= 1
       if (valid < 128) {
 #pragma unroll
         for (int t = 0; t < 128; ++t) s[t] = t < valid ? s[t] : -INFINITY;
       }
-      float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
+      // Exponentials in the log2 domain, scale/shift FMA and row-sum adds packed as fp32x2
+      // (FFMA2 / FADD2); P (bf16) overwrites the first 64 columns of this row's S.
+      // For j > 0 the pass runs SPECULATIVELY against the reference carried over from the previous
+      // tiles while the tile's own maximum is collected in the shadow of the MUFU-paced loop
+      // (pipeline trace, scripts/attn_trace.py: the separate max pass cost 345 of the 2144 cycles
+      // between "S ready" and "P published", all of it on the kernel's critical chain).  The
+      // reference is validated afterwards; if some row outgrew it by more than 2^8 — always on the
+      // first tile, rarely later — O and l move to the new reference and the pass is redone from
+      // the registers.
+      const uint64_t scale2 = pack_f32x2(scale, scale);
+      uint64_t acc_a = 0ull, acc_b = 0ull;  // (0.f, 0.f)
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      auto exp_pass = [&](float neg_m, bool track_max) {
+        const uint64_t negm2 = pack_f32x2(neg_m, neg_m);
 #pragma unroll
-      for (int t = 4; t < 128; t += 4) {
-        m0 = fmaxf(m0, s[t]);
-        m1 = fmaxf(m1, s[t + 1]);
-        m2 = fmaxf(m2, s[t + 2]);
-        m3 = fmaxf(m3, s[t + 3]);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int t = 0; t < 32; t += 4) {
+            const float s0 = s[c * 32 + t], s1 = s[c * 32 + t + 1], s2 = s[c * 32 + t + 2],
+                        s3 = s[c * 32 + t + 3];
+            if (track_max) {
+              m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1); m2 = fmaxf(m2, s2); m3 = fmaxf(m3, s3);
+            }
+            float x0, x1, x2, x3;
+            unpack_f32x2(ffma2(pack_f32x2(s0, s1), scale2, negm2), x0, x1);
+            unpack_f32x2(ffma2(pack_f32x2(s2, s3), scale2, negm2), x2, x3);
+            const float e0 = fast_exp2(x0);
+            const float e1 = fast_exp2(x1);
+            const float e2 = fast_exp2(x2);
+            const float e3 = fast_exp2(x3);
+            acc_a = fadd2(acc_a, pack_f32x2(e0, e1));
+            acc_b = fadd2(acc_b, pack_f32x2(e2, e3));
+            pk[t / 2] = pack_bf16x2(e0, e1);
+            pk[t / 2 + 1] = pack_bf16x2(e2, e3);
+          }
+          tmem_st16(tS + c * 16, pk);
+        }
+      };
+      if (j > 0) {
+        exp_pass(-m_used * scale, true);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 128; t += 4) {
+          m0 = fmaxf(m0, s[t]);
+          m1 = fmaxf(m1, s[t + 1]);
+          m2 = fmaxf(m2, s[t + 2]);
+          m3 = fmaxf(m3, s[t + 3]);
+        }
       }
       const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 2);  // pass 1 done
       // lazy rescale: only when some row of this warp grew its max by more than 2^8
       const bool grow = (m_tile - m_used) * scale > 8.0f;  // true on the first tile (m_used=-inf)
       if (__any_sync(0xffffffffu, grow)) {
@@ -252,41 +315,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st32(tO + c * 32, r);
           }
         }
-      }
-      // exponentials in the log2 domain; the scale/shift FMA and the row-sum adds are packed
-      // fp32x2 (FFMA2 / FADD2): the loop is bound by the issue rate of a single warp per
-      // scheduler (ncu: profiles/), so instructions per element are what matter
-      const float neg_m = -m_used * scale;
-      const uint64_t scale2 = pack_f32x2(scale, scale);
-      const uint64_t negm2 = pack_f32x2(neg_m, neg_m);
-      uint64_t acc_a = 0ull, acc_b = 0ull;  // (0.f, 0.f)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int t = 0; t < 32; t += 4) {
-          float x0, x1, x2, x3;
-          unpack_f32x2(ffma2(pack_f32x2(s[c * 32 + t], s[c * 32 + t + 1]), scale2, negm2), x0, x1);
-          unpack_f32x2(ffma2(pack_f32x2(s[c * 32 + t + 2], s[c * 32 + t + 3]), scale2, negm2), x2, x3);
-          const float e0 = fast_exp2(x0);
-          const float e1 = fast_exp2(x1);
-          const float e2 = fast_exp2(x2);
-          const float e3 = fast_exp2(x3);
-          acc_a = fadd2(acc_a, pack_f32x2(e0, e1));
-          acc_b = fadd2(acc_b, pack_f32x2(e2, e3));
-          pk[t / 2] = pack_bf16x2(e0, e1);
-          pk[t / 2 + 1] = pack_bf16x2(e2, e3);
-        }
-        tmem_st16(tS + c * 16, pk);
+        acc_a = 0ull;
+        acc_b = 0ull;
+        exp_pass(-m_used * scale, false);
       }
       float a0, a1, a2, a3;
       unpack_f32x2(acc_a, a0, a1);
       unpack_f32x2(acc_b, a2, a3);
       l_sum += (a0 + a1) + (a2 + a3);
+      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 3);  // exps issued
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[wg]);
+      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 4);  // P published
     }
 
     // ---- epilogue: O / l -> bf16 -> global (one 256-byte row segment per thread)
@@ -330,6 +372,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 }  // namespace ovb
+
+#ifdef OVB_ATTN_TRACE
+extern "C" int ovb_attn_set_trace(long long* dev_buf) {
+  return cudaMemcpyToSymbol(ovb::g_attn_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
   using namespace ovb;

@@ -372,6 +372,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// Same result as pack_bf16x2 for finite non-negative inputs (round to nearest even), but built from
+// integer ALU instructions: F2FP shares the 16-op/clk XU pipe with MUFU.EX2, which is the pacing
+// unit of the attention softmax (scripts/attn_trace.py).
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  const uint32_t a = __float_as_uint(lo), b = __float_as_uint(hi);
+  const uint32_t ra = a + 0x7FFFu + ((a >> 16) & 1u);
+  const uint32_t rb = b + 0x7FFFu + ((b >> 16) & 1u);
+  return __byte_perm(ra, rb, 0x7632);  // {rb.hi16, ra.hi16}
+}
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
