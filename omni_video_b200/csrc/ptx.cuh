@@ -38,14 +38,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// Suspend-time hint (ns): a waiting thread stays parked in hardware until the phase completes or
+// this much time has passed, instead of returning early and re-issuing the poll loop on a
+// scheduler it shares with working warps.
+#ifndef OVB_MBAR_HINT_NS
+#define OVB_MBAR_HINT_NS 20000
+#endif
+constexpr uint32_t kMbarSuspendHintNs = OVB_MBAR_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs)
       : "memory");
   return ok != 0;
 }
@@ -372,14 +379,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// Same result as pack_bf16x2 for finite non-negative inputs (round to nearest even), but built from
-// integer ALU instructions: F2FP shares the 16-op/clk XU pipe with MUFU.EX2, which is the pacing
-// unit of the attention softmax (scripts/attn_trace.py).
+// bf16x2 pack on the integer ALU pipe: add half an ulp and keep the high halves (round to nearest,
+// ties away from zero: differs from F2FP's ties-to-even only on exact ties, 2^-16 of the inputs;
+// valid for finite values).  F2FP shares the XU pipe (4 lanes/clk per scheduler) with MUFU.EX2,
+// and the softmax loop is bound by exactly that pipe: 1 MUFU + 0.5 F2FP per element = 12 cycles
+// per element per warp (measured 1536 cycles per 128-element row pass, scripts/attn_trace.py).
 __device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
-  const uint32_t a = __float_as_uint(lo), b = __float_as_uint(hi);
-  const uint32_t ra = a + 0x7FFFu + ((a >> 16) & 1u);
-  const uint32_t rb = b + 0x7FFFu + ((b >> 16) & 1u);
-  return __byte_perm(ra, rb, 0x7632);  // {rb.hi16, ra.hi16}
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
@@ -426,6 +432,22 @@ __device__ __forceinline__ float poly_exp2(float x) {
   p = fmaf(p, f, 0.6932609677314758f);
   p = fmaf(p, f, 0.9999280571937561f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+// Two lanes at once (FFMA2 / FADD2).  Inputs must be >= -120 (callers clamp).
+__device__ __forceinline__ uint64_t poly_exp2_x2(uint64_t x) {
+  const uint64_t r = fadd2(x, pack_f32x2(12582912.0f, 12582912.0f));
+  const uint64_t n = fadd2(r, pack_f32x2(-12582912.0f, -12582912.0f));
+  const uint64_t f = ffma2(n, pack_f32x2(-1.f, -1.f), x);
+  uint64_t p = ffma2(f, pack_f32x2(0.0551716685295105f, 0.0551716685295105f),
+                     pack_f32x2(0.2426111251115799f, 0.2426111251115799f));
+  p = ffma2(p, f, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, pack_f32x2(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1, r0, r1;
+  unpack_f32x2(p, p0, p1);
+  unpack_f32x2(r, r0, r1);
+  return pack_f32x2(__int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23)),
+                    __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23)));
 }
 
 // GELU(tanh) exactly as torch.nn.GELU(approximate='tanh') evaluates it in fp32.

@@ -12,13 +12,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from omni_video_b200 import _lib  # noqa: E402
 
-lib = C.CDLL(os.path.join(ROOT, "scripts", "microbench", "build", "libovb_trace.so"))
+lib = C.CDLL(os.path.join(ROOT, "scripts", "microbench", "build", os.environ.get("OVB_TRACE_LIB", "libovb_trace.so")))
 lib.ovb_attn_fwd.restype = C.c_int
 lib.ovb_attn_fwd.argtypes = [C.POINTER(_lib.AttnArgs), C.c_void_p]
 lib.ovb_attn_set_trace.argtypes = [C.c_void_p]
 bf16 = torch.bfloat16
-L, H = 32760, 12
-q, k, v = (torch.randn(1, L, H, 128, device="cuda").to(bf16) for _ in range(3))
+L, H = int(os.environ.get("OVB_TRACE_L", "32760")), int(os.environ.get("OVB_TRACE_H", "12"))
+LQ = int(os.environ.get("OVB_TRACE_LQ", str(L)))
+q = torch.randn(1, LQ, H, 128, device="cuda").to(bf16)
+k, v = (torch.randn(1, L, H, 128, device="cuda").to(bf16) for _ in range(2))
 out = torch.empty_like(q)
 trace = torch.zeros(8 * 32, dtype=torch.int64, device="cuda")
 lib.ovb_attn_set_trace(C.c_void_p(trace.data_ptr()))
@@ -26,8 +28,9 @@ a = _lib.AttnArgs()
 for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
     setattr(a, name, t.data_ptr())
 a.q_row_stride = a.k_row_stride = a.v_row_stride = a.o_row_stride = H * 128
-a.q_batch_stride = a.k_batch_stride = a.v_batch_stride = a.o_batch_stride = L * H * 128
-a.B, a.H, a.Lq, a.Lk = 1, H, L, L
+a.k_batch_stride = a.v_batch_stride = L * H * 128
+a.q_batch_stride = a.o_batch_stride = LQ * H * 128
+a.B, a.H, a.Lq, a.Lk = 1, H, LQ, L
 for _ in range(2):
     rc = lib.ovb_attn_fwd(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0

@@ -1,0 +1,100 @@
+// Microbenchmark: cycles per element of the attention softmax inner loop variants, one warp per
+// scheduler (4 warps per CTA, one CTA per SM), data in registers.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o softmax_rate softmax_rate.cu -I ../../omni_video_b200/csrc
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "ptx.cuh"
+using namespace ovb;
+
+__device__ __forceinline__ uint64_t poly_exp2_x2(uint64_t x) {
+  // two lanes at once: 2^x, x <= 0 (no clamp: caller guarantees x >= -120)
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+  const uint64_t nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+  const uint64_t r = fadd2(x, magic);
+  const uint64_t n = fadd2(r, nmagic);
+  // f = x - n  ->  x + (-1)*n
+  const uint64_t f = ffma2(n, pack_f32x2(-1.f, -1.f), x);
+  uint64_t p = ffma2(f, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.2426111251f, 0.2426111251f));
+  p = ffma2(p, f, pack_f32x2(0.6932609677f, 0.6932609677f));
+  p = ffma2(p, f, pack_f32x2(0.9999280572f, 0.9999280572f));
+  float p0, p1, r0, r1;
+  unpack_f32x2(p, p0, p1);
+  unpack_f32x2(r, r0, r1);
+  const float y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  const float y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+  return pack_f32x2(y0, y1);
+}
+
+template <int V>
+__global__ void __launch_bounds__(128, 1) k(const float* in, uint32_t* out, int iters, long long* cycles) {
+  float s[128];
+#pragma unroll
+  for (int t = 0; t < 128; ++t) s[t] = in[(threadIdx.x * 131 + t * 7) & 1023];
+  const float scale = 0.127f, neg_m = -0.73f;
+  const uint64_t scale2 = pack_f32x2(scale, scale), negm2 = pack_f32x2(neg_m, neg_m);
+  uint64_t acc_a = 0ull, acc_b = 0ull;
+  uint32_t sink = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int t = 0; t < 128; t += 4) {
+      float x0, x1, x2, x3;
+      const uint64_t xa = ffma2(pack_f32x2(s[t], s[t + 1]), scale2, negm2);
+      const uint64_t xb = ffma2(pack_f32x2(s[t + 2], s[t + 3]), scale2, negm2);
+      unpack_f32x2(xa, x0, x1);
+      unpack_f32x2(xb, x2, x3);
+      float e0, e1, e2, e3;
+      if (V == 4 || V == 6) {            // half poly (packed), half MUFU
+        unpack_f32x2(poly_exp2_x2(xa), e0, e1);
+        e2 = fast_exp2(x2); e3 = fast_exp2(x3);
+      } else if (V == 5) {     // all poly
+        unpack_f32x2(poly_exp2_x2(xa), e0, e1);
+        unpack_f32x2(poly_exp2_x2(xb), e2, e3);
+      } else if (V == 7) {     // quarter poly: only every other group of 4 uses a packed poly pair
+        if ((t & 4) == 0) unpack_f32x2(poly_exp2_x2(xa), e0, e1); else { e0 = fast_exp2(x0); e1 = fast_exp2(x1); }
+        e2 = fast_exp2(x2); e3 = fast_exp2(x3);
+      } else {
+        e0 = fast_exp2(x0); e1 = fast_exp2(x1); e2 = fast_exp2(x2); e3 = fast_exp2(x3);
+      }
+      if (V != 1 && V != 2) {
+        acc_a = fadd2(acc_a, pack_f32x2(e0, e1));
+        acc_b = fadd2(acc_b, pack_f32x2(e2, e3));
+      }
+      if (V == 0 || V == 4 || V == 5 || V == 7) { sink ^= pack_bf16x2(e0, e1); sink ^= pack_bf16x2(e2, e3); }
+      else if (V == 3 || V == 6) { sink ^= pack_bf16x2_alu(e0, e1); sink ^= pack_bf16x2_alu(e2, e3); }
+      else { sink ^= __float_as_uint(e0) ^ __float_as_uint(e1) ^ __float_as_uint(e2) ^ __float_as_uint(e3); }
+      s[t] += 1e-3f * __uint_as_float(sink & 0x3f800000u);   // loop-carried so iterations are not hoisted
+    }
+  }
+  const long long t1 = clock64();
+  float a0, a1, a2, a3;
+  unpack_f32x2(acc_a, a0, a1); unpack_f32x2(acc_b, a2, a3);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sink ^ __float_as_uint(a0 + a1 + a2 + a3);
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int V>
+void run(const char* name, const float* in, uint32_t* out, long long* dc) {
+  const int iters = 200;
+  for (int rep = 0; rep < 2; ++rep) k<V><<<148, 128>>>(in, out, iters, dc);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s error %s\n", name, cudaGetErrorString(e)); return; }
+  long long hc[148]; cudaMemcpy(hc, dc, sizeof(hc), cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < 148; ++i) avg += hc[i]; avg /= 148;
+  printf("%-58s %7.2f cycles/element/warp  (%5.0f per 128-element row pass)\n", name, avg / iters / 128, avg / iters);
+}
+
+int main() {
+  float* in; uint32_t* out; long long* dc;
+  cudaMalloc(&in, 4096); cudaMemset(in, 0, 4096); cudaMalloc(&out, 148 * 128 * 4); cudaMalloc(&dc, 148 * 8);
+  run<1>("V1 FFMA2 + MUFU.EX2 only", in, out, dc);
+  run<2>("V2 same (no add, no pack)", in, out, dc);
+  run<0>("V0 FFMA2 + MUFU + FADD2 + F2FP (current loop)", in, out, dc);
+  run<3>("V3 FFMA2 + MUFU + FADD2 + IADD/PRMT pack", in, out, dc);
+  run<7>("V7 25% packed poly + 75% MUFU, F2FP pack", in, out, dc);
+  run<4>("V4 50% packed poly + 50% MUFU, F2FP pack", in, out, dc);
+  run<6>("V6 50% packed poly + 50% MUFU, IADD/PRMT pack", in, out, dc);
+  run<5>("V5 100% packed poly, F2FP pack", in, out, dc);
+  return 0;
+}
