@@ -183,7 +183,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         issue_qk(0, s);
         umma_commit(&s_full[0]);
         OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 1);   // MMA: QK0 issued
+#ifdef OVB_ATTN_ONE_TILE
+        if (j > 0) umma_commit(&v_empty[(j - 1) % kKVStages]);
+        if (false) {
+#else
         if (j > 0) {
+#endif
           const int sp = (j - 1) % kKVStages;
           mbar_wait(&p_full[1], (j - 1) & 1);
           tc_fence_after();
@@ -191,8 +196,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           issue_pv(1, sp, j - 1 == 0);
           umma_commit(&v_empty[sp]);
         }
+#ifndef OVB_ATTN_ONE_TILE
         issue_qk(1, s);
         umma_commit(&s_full[1]);
+#endif
         umma_commit(&k_empty[s]);
         OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 3);   // MMA: QK1(j) issued
         mbar_wait(&p_full[0], j & 1);
@@ -203,6 +210,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 5);   // MMA: PV0(j) issued
       }
       umma_commit(&o_full[0]);
+#ifdef OVB_ATTN_ONE_TILE
+      umma_commit(&v_empty[(n_kv - 1) % kKVStages]);
+      if (false)
+#endif
       {
         const int sp = (n_kv - 1) % kKVStages;
         mbar_wait(&p_full[1], (n_kv - 1) & 1);
@@ -264,9 +275,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
       auto exp_pass = [&](float neg_m, bool track_max) {
         const uint64_t negm2 = pack_f32x2(neg_m, neg_m);
+#ifdef OVB_ATTN_STTM_LATE
+        uint32_t pk_all[64];
+#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+#ifdef OVB_ATTN_STTM_LATE
+          uint32_t* pk = pk_all + c * 16;
+#else
           uint32_t pk[16];
+#endif
 #pragma unroll
           for (int t = 0; t < 32; t += 4) {
             const float s0 = s[c * 32 + t], s1 = s[c * 32 + t + 1], s2 = s[c * 32 + t + 2],
@@ -299,8 +317,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             pk[t / 2] = pack_bf16x2(e0, e1);
             pk[t / 2 + 1] = pack_bf16x2(e2, e3);
           }
+#ifndef OVB_ATTN_STTM_LATE
           tmem_st16(tS + c * 16, pk);
+#endif
         }
+#ifdef OVB_ATTN_STTM_LATE
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st16(tS + c * 16, pk_all + c * 16);
+#endif
       };
       if (j > 0) {
         exp_pass(-m_used * scale, true);
@@ -355,15 +379,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 4);  // P published
     };
     const int n_full = k_len >> 7;  // tiles with all 128 keys valid
+#ifdef OVB_ATTN_ONE_TILE
+    if (wg == 0) {
+#endif
 #pragma unroll 1
     for (int j = 0; j < n_full; ++j) process_tile(j, std::false_type{});
     if (n_full < n_kv) process_tile(n_full, std::true_type{});
+#ifdef OVB_ATTN_ONE_TILE
+    }
+#endif
 
     // ---- epilogue: O / l -> bf16 -> global (one 256-byte row segment per thread)
     const bool row_ok = q_row < p.Lq;
     __nv_bfloat16* orow = p.out + static_cast<long long>(batch) * p.o_batch_stride +
                           static_cast<long long>(q_row) * p.o_row_stride + head * 128;
+#ifdef OVB_ATTN_ONE_TILE
+    if (n_kv > 0 && wg == 0) {
+#else
     if (n_kv > 0) {
+#endif
       mbar_wait(&o_full[wg], 0);
       tc_fence_after();
       const float inv_l = 1.0f / l_sum;

@@ -6,26 +6,7 @@
 #include "ptx.cuh"
 using namespace ovb;
 
-__device__ __forceinline__ uint64_t poly_exp2_x2(uint64_t x) {
-  // two lanes at once: 2^x, x <= 0 (no clamp: caller guarantees x >= -120)
-  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
-  const uint64_t nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
-  const uint64_t r = fadd2(x, magic);
-  const uint64_t n = fadd2(r, nmagic);
-  // f = x - n  ->  x + (-1)*n
-  const uint64_t f = ffma2(n, pack_f32x2(-1.f, -1.f), x);
-  uint64_t p = ffma2(f, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.2426111251f, 0.2426111251f));
-  p = ffma2(p, f, pack_f32x2(0.6932609677f, 0.6932609677f));
-  p = ffma2(p, f, pack_f32x2(0.9999280572f, 0.9999280572f));
-  float p0, p1, r0, r1;
-  unpack_f32x2(p, p0, p1);
-  unpack_f32x2(r, r0, r1);
-  const float y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
-  const float y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
-  return pack_f32x2(y0, y1);
-}
-
-template <int V>
+template <int V, int REP = 1>
 __global__ void __launch_bounds__(128, 1) k(const float* in, uint32_t* out, int iters, long long* cycles) {
   float s[128];
 #pragma unroll
@@ -37,6 +18,8 @@ __global__ void __launch_bounds__(128, 1) k(const float* in, uint32_t* out, int 
   __syncthreads();
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < REP; ++rep)
 #pragma unroll
     for (int t = 0; t < 128; t += 4) {
       float x0, x1, x2, x3;
@@ -74,20 +57,26 @@ __global__ void __launch_bounds__(128, 1) k(const float* in, uint32_t* out, int 
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
-template <int V>
+template <int V, int REP = 1>
 void run(const char* name, const float* in, uint32_t* out, long long* dc) {
-  const int iters = 200;
-  for (int rep = 0; rep < 2; ++rep) k<V><<<148, 128>>>(in, out, iters, dc);
+  const int iters = 200 / REP;
+  for (int rep = 0; rep < 2; ++rep) k<V, REP><<<148, 128>>>(in, out, iters, dc);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%s error %s\n", name, cudaGetErrorString(e)); return; }
   long long hc[148]; cudaMemcpy(hc, dc, sizeof(hc), cudaMemcpyDeviceToHost);
   double avg = 0; for (int i = 0; i < 148; ++i) avg += hc[i]; avg /= 148;
-  printf("%-58s %7.2f cycles/element/warp  (%5.0f per 128-element row pass)\n", name, avg / iters / 128, avg / iters);
+  printf("%-58s %7.2f cycles/element/warp  (%5.0f per 128-element row pass)\n", name, avg / iters / 128 / REP, avg / iters / REP);
 }
 
 int main() {
   float* in; uint32_t* out; long long* dc;
   cudaMalloc(&in, 4096); cudaMemset(in, 0, 4096); cudaMalloc(&out, 148 * 128 * 4); cudaMalloc(&dc, 148 * 8);
+  run<0, 1>("V0 loop body  8 KB of code", in, out, dc);
+  run<0, 2>("V0 loop body 16 KB of code (2 copies)", in, out, dc);
+  run<0, 4>("V0 loop body 32 KB of code (4 copies)", in, out, dc);
+  run<0, 8>("V0 loop body 64 KB of code (8 copies)", in, out, dc);
+  run<5, 1>("V5 all-poly body 1 copy", in, out, dc);
+  run<5, 4>("V5 all-poly body 4 copies", in, out, dc);
   run<1>("V1 FFMA2 + MUFU.EX2 only", in, out, dc);
   run<2>("V2 same (no add, no pack)", in, out, dc);
   run<0>("V0 FFMA2 + MUFU + FADD2 + F2FP (current loop)", in, out, dc);
