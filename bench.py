@@ -5,7 +5,7 @@
 
 One *step* is what the reference's sampling loop does per timestep (x2x_gen_unified.py:474-492):
 two `WanModel.forward` calls (conditional + unconditional, B=1 each), the classifier-free-guidance
-combine and the sampler's latent update.  At N=1 the workload is BASELINE.json `configs[1]`:
+combine and the flow-matching UniPC update of the latent (utils/fm_solvers_unipc.py).  At N=1 the workload is BASELINE.json `configs[1]`:
 OmniVideo2-1.3B, 81x480x832 video = latent [16,21,60,104] = 32760 tokens, bf16, random-init weights
 of that architecture, synthetic N(0,1) latents / text context (no checkpoints or datasets offline).
 
@@ -170,11 +170,19 @@ class Stepper:
         self.torch, self.model, self.seq_len = torch, model, seq_len
         self.world, self.rank = world, rank
         self.cfg_groups = cfg_groups  # None, or (my_branch, pair_group) when cond/uncond are split
-        self.sigmas = torch.linspace(1.0, 0.0, 51).tolist()
+        # the reference's sampler: flow-matching UniPC, 50 steps, shift 5 (x2x_gen_unified.py:409-416,
+        # tools/inference/inference_omni_t2v.sh:43-53); ours runs each tensor expression as one launch
+        from omni_video_b200.utils.fm_solvers_unipc import FlowUniPCMultistepScheduler
+        self.sched = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        self.sched_pos = 50
 
     def step(self, latent, ctx_c, ctx_u, i):
         torch = self.torch
-        t = torch.full((1,), int(self.sigmas[i % 50] * 1000), device=latent.device, dtype=torch.int64)
+        if self.sched_pos >= 50:  # a fresh 50-step schedule (the bench runs fewer steps than one sample needs)
+            self.sched.set_timesteps(50, device=latent.device, shift=5.0)
+            self.sched_pos = 0
+        t = self.sched.timesteps[self.sched_pos:self.sched_pos + 1]
+        self.sched_pos += 1
         if self.cfg_groups is None and self.batch_cfg:
             # cond + uncond as ONE forward with B = 2 (WanModel.forward takes lists): same
             # arithmetic per sample, half the launches, and 2x the CTAs per attention launch
@@ -192,9 +200,9 @@ class Stepper:
             both = torch.empty((2,) + tuple(mine.shape), device=mine.device, dtype=mine.dtype)
             dist.all_gather_into_tensor(both, mine.contiguous(), group=pair)
             cond, uncond = both[0], both[1]
-        noise_pred = uncond + GUIDE_SCALE * (cond - uncond)                      # :484
-        ds = self.sigmas[i % 50 + 1] - self.sigmas[i % 50]
-        return (latent.float() + ds * noise_pred).to(latent.dtype)               # flow-matching update
+        # noise_pred = uncond + g (cond - uncond) (:484) folded into the scheduler's x0 prediction;
+        # UniC corrector + UniP predictor (:486-491)
+        return self.sched.step_cfg(cond, uncond, GUIDE_SCALE, t[0], latent.unsqueeze(0))[0].squeeze(0)
 
 
 def run_ours(args):
@@ -249,7 +257,7 @@ def run_ours(args):
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1818)
-    latent0 = torch.randn((16, Fr, H, W), generator=gen, device=dev, dtype=torch.float32)
+    latent0 = torch.randn((16, Fr, H, W), generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)  # bf16 latents as x2x_gen_unified.py:382-391
     ctx_c = torch.randn((min(512, args.text_len), 4096), generator=gen, device=dev).to(torch.bfloat16)
     ctx_u = torch.randn((min(512, args.text_len), 4096), generator=gen, device=dev).to(torch.bfloat16)
     stepper = Stepper(model, seq_len, world, rank, cfg_groups,
@@ -375,7 +383,7 @@ def run_ours(args):
                 vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=f"OmniVideo2-{args.model} DiT, {args.video} "
                                      f"(latent 16x{Fr}x{H}x{W}, {L} tokens), text_len {args.text_len}, "
-                                     "step = cond+uncond forward + CFG + flow update, random-init weights",
+                                     "step = cond+uncond forward + CFG + UniPC update, random-init weights",
                             cfg_batched=bool(stepper.batch_cfg),
                             parallelism=(f"ulysses{sp}" + (f"xcfg{cfg_par}" if cfg_par > 1 else "")) if world > 1 else "single",
                             l2="inputs+weights per step (>2.8 GB) exceed the 126 MB L2; no flush needed",

@@ -212,6 +212,26 @@ int ovb_modulation_table(const void* mod, const float* e, float* out, int32_t n_
 int ovb_cast_f32_to_bf16(const float* x, void* out, int64_t n, void* stream);
 int ovb_cast_bf16_to_f32(const void* x, float* out, int64_t n, void* stream);
 
+/* ---- sampler-side linear combinations ------------------------------------------------------------
+ * out[i] = sum_{k < n_terms} c[k] * x[k][i]      fp32 math; each tensor fp32 or bf16; n % 4 == 0.
+ * One launch for each tensor expression of a denoising step outside the DiT: classifier-free guidance
+ * (reference x2x_gen_unified.py:484), x0 prediction (utils/fm_solvers_unipc.py:319-323), UniPC corrector
+ * (:610-623) and predictor (:467-475).  Bit k of round_mask rounds term k to bf16 before the sum
+ * (torch's promotion rule for `0-dim fp32 tensor * bf16 tensor`, which the reference hits when the
+ * latents are bf16). */
+typedef struct ovb_lincomb_args {
+  const void* x[5];
+  float c[5];
+  int32_t is_bf16[5];
+  int32_t n_terms;
+  int32_t round_mask;
+  void* out;
+  int32_t out_is_bf16;
+  int64_t n;
+} ovb_lincomb_args;
+
+int ovb_lincomb(const ovb_lincomb_args* args, void* stream);
+
 /* ==== Wan2.1 causal-3D VAE (reference omnivideo/modules/vae2_1.py) ================================
  * Activations are channels-last bf16 [T, H, W, C] (C a multiple of 16); all frames of a clip are
  * processed in one pass (the reference's chunk loop + feat_cache, vae2_1.py:515-567, is causal zero

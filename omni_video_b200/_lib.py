@@ -94,6 +94,12 @@ class ConvArgs(C.Structure):
     ]
 
 
+class LinCombArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p * 5), ("c", C.c_float * 5), ("is_bf16", C.c_int32 * 5),
+                ("n_terms", C.c_int32), ("round_mask", C.c_int32), ("out", C.c_void_p),
+                ("out_is_bf16", C.c_int32), ("n", C.c_int64)]
+
+
 # symbol -> (restype, argtypes); every symbol declared in include/ovb200.h must be listed here
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 _SIGNATURES = {
@@ -116,6 +122,7 @@ _SIGNATURES = {
                                            C.c_void_p]),
     "ovb_modulation_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "ovb_lincomb": (C.c_int, [C.POINTER(LinCombArgs), C.c_void_p]),
     "ovb_conv3d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "ovb_rmsnorm_silu_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_int32, C.c_void_p]),

@@ -504,3 +504,85 @@ extern "C" int ovb_modulation_table(const void* mod, const float* e, float* out,
   count_launch();
   return OVB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// out[i] = sum_k c[k] * x_k[i]   (up to 5 terms, fp32 math, fp32 or bf16 tensors).
+// The sampler side of a denoising step is nothing but such combinations of the latent-sized tensors
+// (classifier-free guidance, x0 prediction, UniPC corrector and predictor: reference
+// x2x_gen_unified.py:484, utils/fm_solvers_unipc.py:319-323, :467-475, :610-623); one launch per
+// combination instead of ~6 ATen kernels each.  round_mask bit k rounds term k to bf16 before the
+// sum (what torch's type promotion does for `0-dim fp32 tensor * bf16 tensor`).
+namespace ovb {
+struct LinCombParams {
+  const void* x[5];
+  float c[5];
+  int is_bf16[5];
+  int n_terms;
+  int round_mask;
+  void* out;
+  int out_bf16;
+  long long n;
+};
+
+__global__ void lincomb_kernel(const LinCombParams p) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= p.n) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k >= p.n_terms) break;
+    float v[4];
+    if (p.is_bf16[k]) {
+      const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.x[k]) + i);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+      const float4 w = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x[k]) + i);
+      v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = p.c[k] * v[j];
+      if ((p.round_mask >> k) & 1) t = bf16_round(t);
+      acc[j] = k == 0 ? t : acc[j] + t;
+    }
+  }
+  if (p.out_bf16) {
+    uint2 o;
+    o.x = pack_bf16x2(acc[0], acc[1]);
+    o.y = pack_bf16x2(acc[2], acc[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + i) = o;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + i) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+}  // namespace ovb
+
+extern "C" int ovb_lincomb(const ovb_lincomb_args* a, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(a != nullptr && a->out != nullptr, "ovb_lincomb: null args");
+  OVB_CHECK_ARG(a->n_terms >= 1 && a->n_terms <= 5, "ovb_lincomb: n_terms=%d outside [1,5]", a->n_terms);
+  OVB_CHECK_ARG(a->n > 0 && a->n % 4 == 0, "ovb_lincomb: n must be a positive multiple of 4");
+  LinCombParams p;
+  uintptr_t align = reinterpret_cast<uintptr_t>(a->out);
+  for (int k = 0; k < 5; ++k) {
+    p.x[k] = k < a->n_terms ? a->x[k] : nullptr;
+    p.c[k] = a->c[k];
+    p.is_bf16[k] = a->is_bf16[k];
+    if (k < a->n_terms) {
+      OVB_CHECK_ARG(a->x[k] != nullptr, "ovb_lincomb: term %d is null", k);
+      align |= reinterpret_cast<uintptr_t>(a->x[k]);
+    }
+  }
+  OVB_CHECK_ARG(align % 16 == 0, "ovb_lincomb: pointers must be 16-byte aligned");
+  p.n_terms = a->n_terms;
+  p.round_mask = a->round_mask;
+  p.out = a->out;
+  p.out_bf16 = a->out_is_bf16;
+  p.n = a->n;
+  lincomb_kernel<<<ew_grid(a->n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}

@@ -344,6 +344,31 @@ def cast_f32_to_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def lincomb(terms, out: Optional[torch.Tensor] = None, out_dtype=None, round_bf16=()) -> torch.Tensor:
+    """out = sum_k c_k * x_k for `terms` = [(c_k, x_k), ...] (<= 5 tensors of one shape, fp32 or bf16).
+    `round_bf16`: indices of terms rounded to bf16 before the sum."""
+    lib = _lib.load()
+    xs = [x for _, x in terms]
+    _need_cuda(*xs, out)
+    assert 1 <= len(terms) <= 5
+    ref = xs[0]
+    for x in xs:
+        assert x.shape == ref.shape and x.is_contiguous() and x.dtype in (f32, bf16)
+    if out is None:
+        out = torch.empty(ref.shape, device=ref.device, dtype=out_dtype or ref.dtype)
+    assert out.shape == ref.shape and out.is_contiguous() and out.dtype in (f32, bf16)
+    a = _lib.LinCombArgs()
+    for k, (c, x) in enumerate(terms):
+        a.x[k] = x.data_ptr()
+        a.c[k] = float(c)
+        a.is_bf16[k] = int(x.dtype == bf16)
+    a.n_terms = len(terms)
+    a.round_mask = sum(1 << k for k in round_bf16)
+    a.out, a.out_is_bf16, a.n = out.data_ptr(), int(out.dtype == bf16), ref.numel()
+    _lib.check(lib.ovb_lincomb(C.byref(a), _stream()), "ovb_lincomb")
+    return out
+
+
 # --------------------------------------------------------------------------------- host helpers
 def rope_cos_sin_table(max_len: int = 1024, head_dim: int = 128, theta: float = 10000.0) -> torch.Tensor:
     """fp32 [max_len, head_dim/2, 2] (cos, sin) of the reference's complex `freqs` table
