@@ -27,6 +27,9 @@ namespace ovb {
 #define OVB_ATTN_POLY 0   // percentage of exponentials evaluated by the FMA-pipe polynomial (0, 50, 100)
 #endif
 
+#ifndef OVB_TRACE_QUAD
+#define OVB_TRACE_QUAD 0
+#endif
 #ifdef OVB_ATTN_TRACE
 // Debug build only (scripts/attn_trace.py): clock64() stamps of one CTA's pipeline events.
 __device__ long long* g_attn_trace = nullptr;
@@ -154,6 +157,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ka = k_addr + s * kTileBytes;
         const uint32_t d = tmem_base + (i == 0 ? kColS0 : kColS1);
 #pragma unroll
+#ifdef OVB_ATTN_NO_MMA
+        return;
+#endif
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
           umma_ss(d, umma_desc_sw128(qa + off, 16, 1024), umma_desc_sw128(ka + off, 16, 1024),
@@ -165,6 +171,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t pt = tmem_base + (i == 0 ? kColS0 : kColS1);
         const uint32_t d = tmem_base + (i == 0 ? kColO0 : kColO1);
 #pragma unroll
+#ifdef OVB_ATTN_NO_MMA
+        return;
+#endif
         for (int kk = 0; kk < 8; ++kk) {
           // 16 kv rows per MMA: 2048 B down the V tile; second 64 columns are kBoxBytes away (LBO)
           umma_ts(d, pt + kk * 8, umma_desc_sw128(va + kk * 2048, kBoxBytes, 1024), idesc_pv,
@@ -245,7 +254,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr bool kMask = decltype(mask_tag)::value;
       mbar_wait(&s_full[wg], j & 1);
       tc_fence_after();
-      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 0);  // S seen
+      OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 0);  // S seen
       float s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -255,7 +264,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int t = 0; t < 32; ++t) s[c * 32 + t] = __uint_as_float(r[t]);
       }
       tmem_wait_ld();
-      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 1);  // S loaded
+      OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 1);  // S loaded
       if constexpr (kMask) {
         const int valid = k_len - j * 128;  // 1..127
 #pragma unroll
@@ -326,9 +335,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int c = 0; c < 4; ++c) tmem_st16(tS + c * 16, pk_all + c * 16);
 #endif
       };
+#ifdef OVB_ATTN_NO_TRACKMAX
+      if (j > 0) {
+        exp_pass(-m_used * scale, false);
+        m0 = m_used;
+      } else {
+#else
       if (j > 0) {
         exp_pass(-m_used * scale, true);
       } else {
+#endif
 #pragma unroll
         for (int t = 0; t < 128; t += 4) {
           m0 = fmaxf(m0, s[t]);
@@ -338,7 +354,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 2);  // pass 1 done
+      OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 2);  // pass 1 done
       // lazy rescale: only when some row of this warp grew its max by more than 2^8
       const bool grow = (m_tile - m_used) * scale > 8.0f;  // true on the first tile (m_used=-inf)
       if (__any_sync(0xffffffffu, grow)) {
@@ -371,12 +387,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       unpack_f32x2(acc_a, a0, a1);
       unpack_f32x2(acc_b, a2, a3);
       l_sum += (a0 + a1) + (a2 + a3);
-      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 3);  // exps issued
+      OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 3);  // exps issued
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[wg]);
-      OVB_TRACE(j >= 64 && j < 72 && quad == 0 && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 4);  // P published
+      OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 4);  // P published
     };
     const int n_full = k_len >> 7;  // tiles with all 128 keys valid
 #ifdef OVB_ATTN_ONE_TILE
