@@ -23,10 +23,6 @@
 
 namespace ovb {
 
-#ifndef OVB_ATTN_POLY
-#define OVB_ATTN_POLY 0   // percentage of exponentials evaluated by the FMA-pipe polynomial (0, 50, 100)
-#endif
-
 #ifndef OVB_TRACE_QUAD
 #define OVB_TRACE_QUAD 0
 #endif
@@ -46,6 +42,7 @@ constexpr int kAttnThreads = 384;
 constexpr int kTileBytes = 128 * 128 * 2;  // 32 KB : one 128x128 bf16 tile (two 64-col TMA boxes)
 constexpr int kBoxBytes = 128 * 64 * 2;    // 16 KB
 constexpr int kKVStages = 2;
+constexpr int kPartSteps = 6;  // PV k-steps (16 keys each) covered by the first P publication
 constexpr int kAttnSmem = 2 * kTileBytes + 2 * kKVStages * kTileBytes + 1024 + 256;
 
 // TMEM column map
@@ -84,7 +81,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = bars + 9;      // [2] per Q tile
   uint64_t* p_full = bars + 11;     // [2] per Q tile
   uint64_t* o_full = bars + 13;     // [2] per Q tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_part = bars + 15;     // [2] per Q tile: P columns of keys [0, 96) published
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,6 +109,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+      mbar_init(&p_part[i], 4);
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -157,28 +156,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ka = k_addr + s * kTileBytes;
         const uint32_t d = tmem_base + (i == 0 ? kColS0 : kColS1);
 #pragma unroll
-#ifdef OVB_ATTN_NO_MMA
-        return;
-#endif
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
           umma_ss(d, umma_desc_sw128(qa + off, 16, 1024), umma_desc_sw128(ka + off, 16, 1024),
                   idesc_qk, kk != 0);
         }
       };
-      auto issue_pv = [&](int i, int s, bool first) {
+      auto issue_pv = [&](int i, int s, bool first, int kk0, int kk1) {
         const uint32_t va = v_addr + s * kTileBytes;
         const uint32_t pt = tmem_base + (i == 0 ? kColS0 : kColS1);
         const uint32_t d = tmem_base + (i == 0 ? kColO0 : kColO1);
-#pragma unroll
-#ifdef OVB_ATTN_NO_MMA
-        return;
-#endif
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = kk0; kk < kk1; ++kk) {
           // 16 kv rows per MMA: 2048 B down the V tile; second 64 columns are kBoxBytes away (LBO)
           umma_ts(d, pt + kk * 8, umma_desc_sw128(va + kk * 2048, kBoxBytes, 1024), idesc_pv,
                   !(first && kk == 0));
         }
+      };
+
+      // O_i += P_i V: k-steps [0,6) as soon as keys [0,96) of P are published, the rest when the
+      // softmax warpgroup has finished the row.
+      auto pv_tile = [&](int i, int s, int jj) {
+        mbar_wait(&p_part[i], jj & 1);
+        tc_fence_after();
+        OVB_TRACE(jj + i >= 64 && jj + i < 72, (jj + i - 64) * 32 + (i == 0 ? 4 : 6));   // MMA: P part seen
+        issue_pv(i, s, jj == 0, 0, kPartSteps);
+        mbar_wait(&p_full[i], jj & 1);
+        tc_fence_after();
+        issue_pv(i, s, jj == 0, kPartSteps, 8);
       };
 
       mbar_wait(q_full, 0);
@@ -192,42 +196,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         issue_qk(0, s);
         umma_commit(&s_full[0]);
         OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 1);   // MMA: QK0 issued
-#ifdef OVB_ATTN_ONE_TILE
-        if (j > 0) umma_commit(&v_empty[(j - 1) % kKVStages]);
-        if (false) {
-#else
         if (j > 0) {
-#endif
           const int sp = (j - 1) % kKVStages;
-          mbar_wait(&p_full[1], (j - 1) & 1);
-          tc_fence_after();
-          OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 2);   // MMA: P1(j-1) seen
-          issue_pv(1, sp, j - 1 == 0);
+          pv_tile(1, sp, j - 1);
+          OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 2);   // MMA: PV1(j-1) issued
           umma_commit(&v_empty[sp]);
         }
-#ifndef OVB_ATTN_ONE_TILE
         issue_qk(1, s);
         umma_commit(&s_full[1]);
-#endif
         umma_commit(&k_empty[s]);
         OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 3);   // MMA: QK1(j) issued
-        mbar_wait(&p_full[0], j & 1);
-        OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 4);   // MMA: P0(j) seen
         mbar_wait(&v_full[s], ph);
-        tc_fence_after();
-        issue_pv(0, s, j == 0);
+        pv_tile(0, s, j);
         OVB_TRACE(j >= 64 && j < 72, (j - 64) * 32 + 5);   // MMA: PV0(j) issued
       }
       umma_commit(&o_full[0]);
-#ifdef OVB_ATTN_ONE_TILE
-      umma_commit(&v_empty[(n_kv - 1) % kKVStages]);
-      if (false)
-#endif
       {
         const int sp = (n_kv - 1) % kKVStages;
-        mbar_wait(&p_full[1], (n_kv - 1) & 1);
-        tc_fence_after();
-        issue_pv(1, sp, n_kv - 1 == 0);
+        pv_tile(1, sp, n_kv - 1);
         umma_commit(&v_empty[sp]);
         umma_commit(&o_full[1]);
       }
@@ -242,109 +228,133 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tO = tmem_base + lane_base + (wg == 0 ? kColO0 : kColO1);
     const int q_row = q_blk * 256 + wg * 128 + quad * 32 + lane;
     const float scale = p.scale_log2;
+    const uint32_t rt_zero = static_cast<uint32_t>(p.Lk) >> 31;  // 0, but not provably so
 
     float m_used = -INFINITY;  // reference max (raw score units) the exponentials are taken against
     float l_sum = 0.f;
 
     // One KV tile of this row.  kMask (only the LAST tile of a sequence whose length is not a
     // multiple of 128) is a compile-time flag on purpose: written as a run-time `if`, the compiler
-    // if-converts the 128 compare+select pairs into EVERY tile's instruction stream (256 of ~750
-    // instructions on the integer pipe, which is one of the two pacing pipes of this loop).
+    // if-converts the 128 compare+select pairs into EVERY tile's instruction stream.
+    //
+    // What paces this loop (scripts/microbench/{xu_rate,tmem_rate}.cu): MUFU.EX2 issues once every
+    // 8 cycles per scheduler, so the 128 exponentials of a row cost >= 1024 cycles — and the two
+    // warpgroups share the schedulers, so a pass that overlaps the other tile's pass sees half that
+    // rate.  tcgen05.st costs ~28 cycles and F2FP ~1.3; neither matters.  The kernel's period is
+    // the chain  QK_i(j) -> softmax_i(j) -> PV_i(j) -> QK_i(j+1), so everything here is about
+    // SHORTENING THE CHAIN, not about instruction count:
+    //   * the row is loaded in two waits (chunk 0 first) so the first exponentials start ~120
+    //     cycles earlier;
+    //   * the pass runs SPECULATIVELY against the reference max carried over from earlier tiles,
+    //     the tile's own maximum being collected in the shadow of the MUFU-paced loop (a separate
+    //     max pass cost 345 cycles on the chain);
+    //   * P is published in two parts: keys [0,96) as soon as their stores have landed, so the
+    //     tensor core starts 6 of the 8 PV k-steps while the last 32 exponentials are still being
+    //     evaluated.  For that the WHOLE tile's maximum must be known at the 3/4 point (nothing
+    //     published may have to be taken back), so chunk 3's maxima are folded into chunks 1-2.
+    // The reference is validated at the 3/4 point; if some row outgrew it by more than 2^8 — always
+    // on the first tile, rarely later — O and l move to the new reference and the pass is redone
+    // from the registers before anything is published.
     auto process_tile = [&](int j, auto mask_tag) {
       constexpr bool kMask = decltype(mask_tag)::value;
       mbar_wait(&s_full[wg], j & 1);
       tc_fence_after();
       OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 0);  // S seen
       float s[128];
+      {
+        uint32_t r[32];
+        tmem_ld32(tS, r);
+        tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+        for (int t = 0; t < 32; ++t) s[t] = __uint_as_float(r[t]);
+      }
+#pragma unroll
+      for (int c = 1; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tS + c * 32, r);
 #pragma unroll
         for (int t = 0; t < 32; ++t) s[c * 32 + t] = __uint_as_float(r[t]);
       }
-      tmem_wait_ld();
-      OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 1);  // S loaded
+      const int valid = k_len - j * 128;  // kMask: 1..127
       if constexpr (kMask) {
-        const int valid = k_len - j * 128;  // 1..127
 #pragma unroll
-        for (int t = 0; t < 128; ++t) s[t] = t < valid ? s[t] : -INFINITY;
+        for (int t = 0; t < 32; ++t) s[t] = t < valid ? s[t] : -INFINITY;
       }
-      // Exponentials in the log2 domain, scale/shift FMA and row-sum adds packed as fp32x2
-      // (FFMA2 / FADD2); P (bf16) overwrites the first 64 columns of this row's S.
-      // For j > 0 the pass runs SPECULATIVELY against the reference carried over from the previous
-      // tiles while the tile's own maximum is collected in the shadow of the MUFU-paced loop
-      // (pipeline trace, scripts/attn_trace.py: the separate max pass cost 345 of the 2144 cycles
-      // between "S ready" and "P published", all of it on the kernel's critical chain).  The
-      // reference is validated afterwards; if some row outgrew it by more than 2^8 — always on the
-      // first tile, rarely later — O and l move to the new reference and the pass is redone from
-      // the registers.
+      // columns 32..127 are in flight until this wait; the "+f" operands pin their first use below it
+      auto wait_rest = [&]() {
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 1; c < 4; ++c) reg_fence32(&s[c * 32]);
+        if constexpr (kMask) {
+#pragma unroll
+          for (int t = 32; t < 128; ++t) s[t] = t < valid ? s[t] : -INFINITY;
+        }
+      };
+      OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 1);  // first chunk loaded
+
       const uint64_t scale2 = pack_f32x2(scale, scale);
       uint64_t acc_a = 0ull, acc_b = 0ull;  // (0.f, 0.f)
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-      auto exp_pass = [&](float neg_m, bool track_max) {
-        const uint64_t negm2 = pack_f32x2(neg_m, neg_m);
-#ifdef OVB_ATTN_STTM_LATE
-        uint32_t pk_all[64];
-#endif
+      // 32 keys: exponentials in the log2 domain, scale/shift FMA and row-sum adds packed as fp32x2
+      // (FFMA2 / FADD2); bf16 P overwrites columns [16c, 16c+16) of this row's S.  `track`: fold
+      // the chunk's own scores — and, for chunks 1 and 2, half of chunk 3's — into the maxima.
+      auto exp_chunk = [&](const int c, const uint64_t negm2, const bool track) {
+        uint32_t pk[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#ifdef OVB_ATTN_STTM_LATE
-          uint32_t* pk = pk_all + c * 16;
-#else
-          uint32_t pk[16];
-#endif
-#pragma unroll
-          for (int t = 0; t < 32; t += 4) {
-            const float s0 = s[c * 32 + t], s1 = s[c * 32 + t + 1], s2 = s[c * 32 + t + 2],
-                        s3 = s[c * 32 + t + 3];
-            if (track_max) {
-              m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1); m2 = fmaxf(m2, s2); m3 = fmaxf(m3, s3);
+        for (int t = 0; t < 32; t += 4) {
+          const float s0 = s[c * 32 + t], s1 = s[c * 32 + t + 1], s2 = s[c * 32 + t + 2],
+                      s3 = s[c * 32 + t + 3];
+          if (track) {
+            m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1); m2 = fmaxf(m2, s2); m3 = fmaxf(m3, s3);
+            if (c == 1 || c == 2) {
+              m0 = fmaxf(m0, s[96 + (c - 1) * 16 + t / 2]);
+              m1 = fmaxf(m1, s[96 + (c - 1) * 16 + t / 2 + 1]);
             }
-            float x0, x1, x2, x3;
-            const uint64_t xa = ffma2(pack_f32x2(s0, s1), scale2, negm2);
-            const uint64_t xb = ffma2(pack_f32x2(s2, s3), scale2, negm2);
-            unpack_f32x2(xa, x0, x1);
-            unpack_f32x2(xb, x2, x3);
-#if OVB_ATTN_POLY == 100
-            float e0, e1, e2, e3;
-            unpack_f32x2(poly_exp2_x2(pack_f32x2(fmaxf(x0, -120.f), fmaxf(x1, -120.f))), e0, e1);
-            unpack_f32x2(poly_exp2_x2(pack_f32x2(fmaxf(x2, -120.f), fmaxf(x3, -120.f))), e2, e3);
-#elif OVB_ATTN_POLY == 50
-            float e0, e1;
-            unpack_f32x2(poly_exp2_x2(pack_f32x2(fmaxf(x0, -120.f), fmaxf(x1, -120.f))), e0, e1);
-            const float e2 = fast_exp2(x2);
-            const float e3 = fast_exp2(x3);
-#else
-            const float e0 = fast_exp2(x0);
-            const float e1 = fast_exp2(x1);
-            const float e2 = fast_exp2(x2);
-            const float e3 = fast_exp2(x3);
-#endif
-            acc_a = fadd2(acc_a, pack_f32x2(e0, e1));
-            acc_b = fadd2(acc_b, pack_f32x2(e2, e3));
-            pk[t / 2] = pack_bf16x2(e0, e1);
-            pk[t / 2 + 1] = pack_bf16x2(e2, e3);
           }
-#ifndef OVB_ATTN_STTM_LATE
-          tmem_st16(tS + c * 16, pk);
-#endif
+          float x0, x1, x2, x3;
+          unpack_f32x2(ffma2(pack_f32x2(s0, s1), scale2, negm2), x0, x1);
+          unpack_f32x2(ffma2(pack_f32x2(s2, s3), scale2, negm2), x2, x3);
+          const float e0 = fast_exp2(x0), e1 = fast_exp2(x1), e2 = fast_exp2(x2), e3 = fast_exp2(x3);
+          acc_a = fadd2(acc_a, pack_f32x2(e0, e1));
+          acc_b = fadd2(acc_b, pack_f32x2(e2, e3));
+          pk[t / 2] = pack_bf16x2(e0, e1);
+          pk[t / 2 + 1] = pack_bf16x2(e2, e3);
         }
-#ifdef OVB_ATTN_STTM_LATE
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_st16(tS + c * 16, pk_all + c * 16);
-#endif
+        tmem_st16(tS + c * 16, pk);
       };
-#ifdef OVB_ATTN_NO_TRACKMAX
+      auto publish = [&](uint64_t* bar) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+      };
+
+      bool redo;
       if (j > 0) {
-        exp_pass(-m_used * scale, false);
-        m0 = m_used;
+        const float neg_m = -m_used * scale;
+        const uint64_t negm2 = pack_f32x2(neg_m, neg_m);
+        exp_chunk(0, negm2, true);
+        wait_rest();
+        exp_chunk(1, negm2, true);
+        exp_chunk(2, negm2, true);
+        const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        // lazy rescale: only when some row of this warp grew its max by more than 2^8
+        redo = __any_sync(0xffffffffu, (m_tile - m_used) * scale > 8.0f);
+        OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 2);  // 3/4 done
+        if (!redo) {
+          // Publish keys [0,96).  Chunk 3's shift is made to depend on the arrival's token (masked
+          // with a run-time zero): without that, ptxas hoists all of chunk 3's FFMA2/MUFU above
+          // the arrive and the early publication is not early at all (seen in the SASS and in
+          // the pipeline trace: "P part seen" coincided with "exps issued").
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          const uint32_t tok = mbar_arrive_token(&p_part[wg], lane == 0);
+          const float neg_m3 = __uint_as_float(__float_as_uint(neg_m) ^ (tok & rt_zero));
+          exp_chunk(3, pack_f32x2(neg_m3, neg_m3), false);
+        }
       } else {
-#else
-      if (j > 0) {
-        exp_pass(-m_used * scale, true);
-      } else {
-#endif
+        wait_rest();
 #pragma unroll
         for (int t = 0; t < 128; t += 4) {
           m0 = fmaxf(m0, s[t]);
@@ -352,13 +362,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           m2 = fmaxf(m2, s[t + 2]);
           m3 = fmaxf(m3, s[t + 3]);
         }
+        redo = true;
       }
-      const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 2);  // pass 1 done
-      // lazy rescale: only when some row of this warp grew its max by more than 2^8
-      const bool grow = (m_tile - m_used) * scale > 8.0f;  // true on the first tile (m_used=-inf)
-      if (__any_sync(0xffffffffu, grow)) {
-        const float m_new = fmaxf(m_used, m_tile);
+      if (redo) {
+        const float m_new = fmaxf(m_used, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         const float alpha = fast_exp2((m_used - m_new) * scale);  // 0 on the first tile
         l_sum *= alpha;
         m_used = m_new;
@@ -381,39 +388,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         acc_a = 0ull;
         acc_b = 0ull;
-        exp_pass(-m_used * scale, false);
+        const float neg_m = -m_used * scale;
+        const uint64_t negm2 = pack_f32x2(neg_m, neg_m);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) exp_chunk(c, negm2, false);
+        publish(&p_part[wg]);
       }
       float a0, a1, a2, a3;
       unpack_f32x2(acc_a, a0, a1);
       unpack_f32x2(acc_b, a2, a3);
       l_sum += (a0 + a1) + (a2 + a3);
       OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 3);  // exps issued
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[wg]);
+      publish(&p_full[wg]);
       OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 4);  // P published
     };
     const int n_full = k_len >> 7;  // tiles with all 128 keys valid
-#ifdef OVB_ATTN_ONE_TILE
-    if (wg == 0) {
-#endif
 #pragma unroll 1
     for (int j = 0; j < n_full; ++j) process_tile(j, std::false_type{});
     if (n_full < n_kv) process_tile(n_full, std::true_type{});
-#ifdef OVB_ATTN_ONE_TILE
-    }
-#endif
 
     // ---- epilogue: O / l -> bf16 -> global (one 256-byte row segment per thread)
     const bool row_ok = q_row < p.Lq;
     __nv_bfloat16* orow = p.out + static_cast<long long>(batch) * p.o_batch_stride +
                           static_cast<long long>(q_row) * p.o_row_stride + head * 128;
-#ifdef OVB_ATTN_ONE_TILE
-    if (n_kv > 0 && wg == 0) {
-#else
     if (n_kv > 0) {
-#endif
       mbar_wait(&o_full[wg], 0);
       tc_fence_after();
       const float inv_l = 1.0f / l_sum;

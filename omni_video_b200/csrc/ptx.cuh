@@ -38,6 +38,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive from the lanes where `pred` holds and return (the low word of) the barrier's state token,
+// 0 elsewhere.  The token is how a caller ORDERS later arithmetic after the arrival: ptxas moves
+// register-only instructions (MUFU, FFMA) freely above an mbarrier.arrive, but not above the
+// producer of a value they consume.
+__device__ __forceinline__ uint32_t mbar_arrive_token(uint64_t* bar, bool pred) {
+  uint32_t tok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 st;\n"
+      "setp.ne.u32 p, %2, 0;\n"
+      "mov.b64 st, 0;\n"
+      "@p mbarrier.arrive.shared::cta.b64 st, [%1];\n"
+      "cvt.u32.u64 %0, st;\n"
+      "}\n"
+      : "=r"(tok)
+      : "r"(smem_u32(bar)), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+  return tok;
+}
 // Suspend-time hint (ns): a waiting thread stays parked in hardware until the phase completes or
 // this much time has passed, instead of returning early and re-issuing the poll loop on a
 // scheduler it shares with working warps.
@@ -369,6 +389,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+// Compiler-level fence on 32 registers: an empty volatile asm that "rewrites" them, so that no use
+// of these values can be scheduled above the preceding volatile asm (a tcgen05.wait::ld whose
+// loads were issued earlier and are still landing in exactly these registers).  Emits nothing.
+__device__ __forceinline__ void reg_fence32(float* r) {
+  asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]), "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]), "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]), "+f"(r[23]), "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]), "+f"(r[30]), "+f"(r[31]));
 }
 __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");

@@ -37,9 +37,10 @@ for _ in range(2):
 torch.cuda.synchronize()
 t = trace.cpu().view(8, 32)
 t0 = int(t[0, 0])
-names = {0: "MMA  issue QK0", 1: "MMA  QK0 issued", 2: "MMA  P1(j-1) seen", 3: "MMA  QK1 issued", 4: "MMA  P0 seen",
-         5: "MMA  PV0 issued", 8: "SM0  S seen", 9: "SM0  S loaded", 10: "SM0  max done", 11: "SM0  exps issued",
-         12: "SM0  P published", 16: "SM1  S seen", 17: "SM1  S loaded", 18: "SM1  max done",
+names = {0: "MMA  issue QK0", 1: "MMA  QK0 issued", 2: "MMA  PV1(j-1) issued", 3: "MMA  QK1 issued",
+         4: "MMA  P0 part seen", 5: "MMA  PV0 issued", 6: "MMA  P1(j-1) part seen",
+         8: "SM0  S seen", 9: "SM0  chunk0 loaded", 10: "SM0  3/4 done", 11: "SM0  exps issued",
+         12: "SM0  P published", 16: "SM1  S seen", 17: "SM1  chunk0 loaded", 18: "SM1  3/4 done",
          19: "SM1  exps issued", 20: "SM1  P published"}
 ev = []
 for j in range(8):
@@ -55,5 +56,5 @@ per_step = (int(t[7, 0]) - int(t[0, 0])) / 7.0
 print(f"cycles per KV step: {per_step:.0f}")
 for j in range(1, 7):
     sm0 = int(t[j, 12]) - int(t[j, 8]); sm1 = int(t[j, 20]) - int(t[j, 16])
-    print(f"j={j+64}: softmax0 S-seen->P-published {sm0}, (load {int(t[j,9])-int(t[j,8])}, max {int(t[j,10])-int(t[j,9])}, "
-          f"exp {int(t[j,11])-int(t[j,10])}, publish {int(t[j,12])-int(t[j,11])}); softmax1 {sm1}")
+    print(f"j={j+64}: softmax0 S-seen->P-published {sm0}, (load0 {int(t[j,9])-int(t[j,8])}, 3/4 {int(t[j,10])-int(t[j,9])}, "
+          f"rest {int(t[j,11])-int(t[j,10])}, publish {int(t[j,12])-int(t[j,11])}); softmax1 {sm1}")

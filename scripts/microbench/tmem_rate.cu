@@ -139,6 +139,108 @@ __global__ void __launch_bounds__(128, 1) k(const float* in, uint32_t* out, int 
   if (warp == 0) tmem_dealloc<512>(tmem_slot);
 }
 
+
+// spread of the polynomial pairs inside a group of 8 pairs (so they interleave with the MUFU pairs)
+__device__ constexpr int kPolyOrder[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+
+// Kernel-like environment around the M4 pass: 384 threads, setmaxnreg 72/216, warps 4-7 (and 8-11 when
+// BOTH) run the pass on their own TMEM quadrant/columns; POLL: lane 0 of warps 0 and 1 sits in a
+// try_wait (suspend hint) on an mbarrier that completes only at the end, like the TMA/MMA threads.
+template <int BOTH, int POLL, int POLY8 = 0>
+__global__ void __launch_bounds__(384, 1) kenv(const float* in, uint32_t* out, int iters, long long* cycles) {
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t done_bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (threadIdx.x == 32) { mbar_init(&done_bar, BOTH ? 8 : 4); fence_barrier_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+    if (POLL && warp < 2 && lane == 0) mbar_wait(&done_bar, 0);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
+    const int wg = (warp - 4) >> 2;
+    if (wg == 0 || BOTH) {
+      const uint32_t tbase = tmem_slot + (static_cast<uint32_t>((warp & 3) * 32) << 16) + wg * 128;
+      {
+        uint32_t r[32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) r[t] = __float_as_uint(in[(threadIdx.x * 131 + (c * 32 + t) * 7) & 1023]);
+          tmem_st32(tbase + c * 32, r);
+        }
+        tmem_wait_st();
+      }
+      float chain = in[lane];
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        float s[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tbase + c * 32, r);
+#pragma unroll
+          for (int t = 0; t < 32; ++t) s[c * 32 + t] = __uint_as_float(r[t]);
+        }
+        tmem_wait_ld();
+        const float scale = 0.127f, neg_m = -0.73f + 1e-6f * it;
+        const uint64_t scale2 = pack_f32x2(scale, scale), negm2 = pack_f32x2(neg_m, neg_m);
+        uint64_t acc_a = 0ull, acc_b = 0ull;
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int t = 0; t < 32; t += 4) {
+            const float s0 = s[c * 32 + t], s1 = s[c * 32 + t + 1], s2 = s[c * 32 + t + 2], s3 = s[c * 32 + t + 3];
+            m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1); m2 = fmaxf(m2, s2); m3 = fmaxf(m3, s3);
+            float x0, x1, x2, x3;
+            unpack_f32x2(ffma2(pack_f32x2(s0, s1), scale2, negm2), x0, x1);
+            unpack_f32x2(ffma2(pack_f32x2(s2, s3), scale2, negm2), x2, x3);
+            // pair index within a group of 8 pairs (16 elements): pairs < POLY8 go to the FMA pipe
+            const int pa = (t / 2) & 7, pb = (t / 2 + 1) & 7;
+            float e0, e1, e2, e3;
+            if (kPolyOrder[pa] < POLY8) unpack_f32x2(poly_exp2_x2(pack_f32x2(fmaxf(x0, -120.f), fmaxf(x1, -120.f))), e0, e1);
+            else { e0 = fast_exp2(x0); e1 = fast_exp2(x1); }
+            if (kPolyOrder[pb] < POLY8) unpack_f32x2(poly_exp2_x2(pack_f32x2(fmaxf(x2, -120.f), fmaxf(x3, -120.f))), e2, e3);
+            else { e2 = fast_exp2(x2); e3 = fast_exp2(x3); }
+            acc_a = fadd2(acc_a, pack_f32x2(e0, e1));
+            acc_b = fadd2(acc_b, pack_f32x2(e2, e3));
+            pk[t / 2] = pack_bf16x2(e0, e1);
+            pk[t / 2 + 1] = pack_bf16x2(e2, e3);
+          }
+          tmem_st16(tbase + 256 + c * 16, pk);
+        }
+        float a0, a1, a2, a3;
+        unpack_f32x2(acc_a, a0, a1); unpack_f32x2(acc_b, a2, a3);
+        chain += (a0 + a1) + (a2 + a3) + fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        tmem_wait_st();
+      }
+      const long long t1 = clock64();
+      out[blockIdx.x * blockDim.x + threadIdx.x] = __float_as_uint(chain);
+      if (threadIdx.x == 128) cycles[blockIdx.x] = t1 - t0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done_bar);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_slot);
+}
+
+template <int BOTH, int POLL, int POLY8 = 0>
+void run_env(const char* name, const float* in, uint32_t* out, long long* dc) {
+  const int iters = 200;
+  for (int rep = 0; rep < 2; ++rep) kenv<BOTH, POLL, POLY8><<<148, 384>>>(in, out, iters, dc);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s error %s\n", name, cudaGetErrorString(e)); return; }
+  long long hc[148]; cudaMemcpy(hc, dc, sizeof(hc), cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < 148; ++i) avg += hc[i]; avg /= 148;
+  printf("%-64s          %7.0f cycles per iteration\n", name, avg / iters);
+}
+
 template <int MODE>
 void run(const char* name, const float* in, uint32_t* out, long long* dc, int active) {
   const int iters = 200;
@@ -156,7 +258,20 @@ int main() {
   cudaMalloc(&in, 4096);
   { float h[1024]; unsigned x = 12345u; for (int i = 0; i < 1024; ++i) { x = x * 1664525u + 1013904223u; h[i] = -80.0f * (float)(x >> 8) / 16777216.0f; }
     cudaMemcpy(in, h, 4096, cudaMemcpyHostToDevice); }
-  cudaMalloc(&out, 148 * 128 * 4); cudaMalloc(&dc, 148 * 8);
+  cudaMalloc(&out, 148 * 384 * 4); cudaMalloc(&dc, 148 * 8);
+  run_env<0, 0>("ENV 384 thr, setmaxnreg, one WG, no pollers (M4 pass)", in, out, dc);
+  run_env<0, 1>("ENV 384 thr, setmaxnreg, one WG, 2 pollers", in, out, dc);
+  run_env<1, 0>("ENV 384 thr, setmaxnreg, both WGs, no pollers", in, out, dc);
+  run_env<1, 1>("ENV 384 thr, setmaxnreg, both WGs, 2 pollers", in, out, dc);
+  run_env<0, 1, 1>("ENV one WG,   12.5% of pairs by polynomial", in, out, dc);
+  run_env<0, 1, 2>("ENV one WG,   25%   of pairs by polynomial", in, out, dc);
+  run_env<0, 1, 3>("ENV one WG,   37.5% of pairs by polynomial", in, out, dc);
+  run_env<0, 1, 4>("ENV one WG,   50%   of pairs by polynomial", in, out, dc);
+  run_env<1, 1, 1>("ENV both WGs, 12.5% of pairs by polynomial", in, out, dc);
+  run_env<1, 1, 2>("ENV both WGs, 25%   of pairs by polynomial", in, out, dc);
+  run_env<1, 1, 3>("ENV both WGs, 37.5% of pairs by polynomial", in, out, dc);
+  run_env<1, 1, 4>("ENV both WGs, 50%   of pairs by polynomial", in, out, dc);
+  run_env<1, 1, 5>("ENV both WGs, 62.5% of pairs by polynomial", in, out, dc);
   for (int active = 4; active >= 1; active -= 3) {
     run<0>("M0 4 x tcgen05.st.32x32b.x16 back to back", in, out, dc, active);
     run<1>("M1 4 x (tcgen05.ld.32x32b.x32 + wait)", in, out, dc, active);
