@@ -184,6 +184,12 @@ int ovb_rmsnorm_rope(const ovb_rmsnorm_rope_args* args, void* stream);
  */
 int ovb_patchify(const void* x, int32_t x_is_bf16, void* tokens, int64_t ldt, int32_t C, int32_t F,
                  int32_t H, int32_t W, void* stream);
+/* General (pt, ph, pw) patch gather for the conditioning front-end: x [C, F, H, W] (fp32 or bf16) ->
+ * tokens bf16 [(F/pt)*(H/ph)*(W/pw), C*pt*ph*pw], column ((c*pt + it)*ph + ih)*pw + iw, i.e. the
+ * im2col of VisualContextAdapter.patch_embedding (reference modules/visual_context_adapter.py:56-58,
+ * :98); the Conv3d itself is then ovb_gemm_bf16 against weight.flatten(1). */
+int ovb_patchify3d(const void* x, int32_t x_is_bf16, void* tokens, int64_t ldt, int32_t C, int32_t F,
+                   int32_t H, int32_t W, int32_t pt, int32_t ph, int32_t pw, void* stream);
 int ovb_unpatchify(const float* y, int64_t ldy, float* out, int32_t C, int32_t F, int32_t Hp,
                    int32_t Wp, void* stream);
 

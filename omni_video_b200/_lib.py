@@ -113,6 +113,8 @@ _SIGNATURES = {
     "ovb_rmsnorm_rope": (C.c_int, [C.POINTER(RmsRopeArgs), C.c_void_p]),
     "ovb_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                C.c_int32, C.c_int32, C.c_void_p]),
+    "ovb_patchify3d": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ovb_unpatchify": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_void_p]),
     "ovb_linear_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

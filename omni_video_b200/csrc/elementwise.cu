@@ -212,6 +212,34 @@ __global__ void patchify_kernel(const T* __restrict__ x, __nv_bfloat16* __restri
   }
 }
 
+// General patch gather: x[C,F,H,W] -> tokens[(F/pt)*(H/ph)*(W/pw), C*pt*ph*pw] bf16, column
+// ((c*pt + it)*ph + ih)*pw + iw = the order of Conv3d.weight.flatten(1) (VisualContextAdapter's
+// patch_embedding, reference modules/visual_context_adapter.py:56-58, :98).  One thread per output
+// element; consecutive threads write consecutive columns of a token (reads are pw-element runs).
+template <typename T>
+__global__ void patchify3d_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ tok,
+                                  long long ldt, int C, int F, int H, int W, int pt, int ph, int pw) {
+  const int Fp = F / pt, Hp = H / ph, Wp = W / pw;
+  const int cols = C * pt * ph * pw;
+  const long long total = static_cast<long long>(Fp) * Hp * Wp * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long token = i / cols;
+    int col = static_cast<int>(i - token * cols);
+    const int iw = col % pw; col /= pw;
+    const int ih = col % ph; col /= ph;
+    const int it = col % pt;
+    const int c = col / pt;
+    long long t = token;
+    const int wp = t % Wp; t /= Wp;
+    const int hp = t % Hp; t /= Hp;
+    const int fp = static_cast<int>(t);
+    const long long src = ((static_cast<long long>(c) * F + (fp * pt + it)) * H + (hp * ph + ih)) * W +
+                          (wp * pw + iw);
+    tok[token * ldt + (i - token * cols)] = __float2bfloat16_rn(static_cast<float>(x[src]));
+  }
+}
+
 // unpatchify: y[L, 4*C] fp32 (column (ph*2+pw)*C + c) -> out[C, F, 2*Hp, 2*Wp]
 __global__ void unpatchify_kernel(const float* __restrict__ y, long long ldy,
                                   float* __restrict__ out, int C, int F, int Hp, int Wp) {
@@ -436,6 +464,32 @@ extern "C" int ovb_patchify(const void* x, int32_t x_is_bf16, void* tokens, int6
     patchify_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float*>(x), reinterpret_cast<__nv_bfloat16*>(tokens), ldt, C, F, H,
         W);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_patchify3d(const void* x, int32_t x_is_bf16, void* tokens, int64_t ldt, int32_t C,
+                              int32_t F, int32_t H, int32_t W, int32_t pt, int32_t ph, int32_t pw,
+                              void* stream) {
+  OVB_CHECK_ARG(x && tokens, "ovb_patchify3d: null pointer");
+  OVB_CHECK_ARG(C > 0 && F > 0 && H > 0 && W > 0 && pt > 0 && ph > 0 && pw > 0,
+                "ovb_patchify3d: bad shape C=%d F=%d H=%d W=%d patch=(%d,%d,%d)", C, F, H, W, pt, ph, pw);
+  // a strided Conv3d floors: trailing voxels that do not fill a patch are dropped
+  OVB_CHECK_ARG(F >= pt && H >= ph && W >= pw,
+                "ovb_patchify3d: F,H,W = %d,%d,%d smaller than patch (%d,%d,%d)", F, H, W, pt, ph, pw);
+  OVB_CHECK_ARG(ldt >= static_cast<int64_t>(C) * pt * ph * pw, "ovb_patchify3d: ldt=%lld too small",
+                static_cast<long long>(ldt));
+  const long long total = static_cast<long long>(F / pt) * (H / ph) * (W / pw) * C * pt * ph * pw;
+  const int grid = ew_grid(total, 256);
+  if (x_is_bf16)
+    patchify3d_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(tokens), ldt, C, F, H,
+        W, pt, ph, pw);
+  else
+    patchify3d_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float*>(x), reinterpret_cast<__nv_bfloat16*>(tokens), ldt, C, F, H, W, pt,
+        ph, pw);
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OVB_OK;

@@ -268,6 +268,20 @@ def patchify(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tenso
     return out
 
 
+def patchify3d(x: torch.Tensor, patch) -> torch.Tensor:
+    """x: [C, F, H, W] fp32/bf16 contiguous -> bf16 [(F//pt)*(H//ph)*(W//pw), C*pt*ph*pw], columns in the
+    order of Conv3d.weight.flatten(1) (a stride=kernel Conv3d is this gather followed by a GEMM)."""
+    _need_cuda(x)
+    lib = _lib.load()
+    assert x.dim() == 4 and x.is_contiguous() and x.dtype in (f32, bf16)
+    pt, ph, pw = (int(v) for v in patch)
+    Cc, F, H, W = x.shape
+    out = torch.empty(((F // pt) * (H // ph) * (W // pw), Cc * pt * ph * pw), device=x.device, dtype=bf16)
+    _lib.check(lib.ovb_patchify3d(_ptr(x), int(x.dtype == bf16), _ptr(out), out.stride(0), Cc, F, H, W,
+                                  pt, ph, pw, _stream()), "ovb_patchify3d")
+    return out
+
+
 def unpatchify(y: torch.Tensor, C_out: int, grid) -> torch.Tensor:
     """y: fp32 [>=F*Hp*Wp, 4*C_out] -> fp32 [C_out, F, 2*Hp, 2*Wp]."""
     _need_cuda(y)

@@ -23,7 +23,7 @@ from .modules import attention as _attention
 from .modules.model import DiTEngine
 
 __all__ = ["patch_reference_model", "patch_reference_module_globals", "patch_reference_vae",
-           "unpatch_reference_model"]
+           "patch_reference_unified", "unpatch_reference_model"]
 
 
 def patch_reference_model(wan_model, sp_group=None):
@@ -82,3 +82,28 @@ def patch_reference_vae(vae):
     vae.encode = types.MethodType(encode, vae)
     vae.decode = types.MethodType(decode, vae)
     return vae
+
+
+def patch_reference_unified(unified, sp_group=None):
+    """`unified`: the reference's `UnifiedWanWithMixedConditionModel`
+    (omnivideo/modules/unified_model.py:13).  Its `wan_model` is patched as above, and its own
+    `forward` — the conditioning front-end (vlm_norm/vlm_proj, VisualContextAdapter, special-token
+    concatenation, truncation) — is rebound to the B200 implementation, which reads the reference
+    instance's parameters and caches the context per sample across the sampling loop."""
+    from .modules import unified_model as U
+    from .modules.visual_context_adapter import visual_context_forward
+    for name in ("wan_model", "vlm_norm", "vlm_proj", "max_context_len"):
+        if not hasattr(unified, name):
+            raise TypeError(f"patch_reference_unified: object has no `{name}`; expected the reference's "
+                            "UnifiedWanWithMixedConditionModel")
+    patch_reference_model(unified.wan_model, sp_group)
+    unified._ctx_cache = {}
+    unified.context_cache_hits = 0
+    unified.context_cache_misses = 0
+    cls = U.UnifiedWanWithMixedConditionModel
+    for name in ("_vlm", "_params_key", "mixed_context", "forward"):
+        setattr(unified, name, types.MethodType(getattr(cls, name), unified))
+    adapter = getattr(unified, "visual_context_adapter", None)
+    if adapter is not None:
+        adapter.forward = types.MethodType(visual_context_forward, adapter)
+    return unified

@@ -185,3 +185,38 @@ def vae_video(shape: Tuple[int, int, int], seed: int = 7) -> torch.Tensor:
     v = 0.5 * torch.sin(0.11 * x + 0.07 * y + 0.3 * t + ph) + 0.3 * torch.cos(0.05 * x - 0.13 * y + ph)
     v = v + 0.05 * _normal(rng, (3, T, H, W), 1.0)
     return v.clamp(-1, 1)
+
+
+# ------------------------------------------------------------------------- conditioning front-end
+def unified_state_dict(cfg: dict, vlm_in_dim: int, adapter_patch=(1, 4, 4), seed: int = 1818,
+                       with_adapter: bool = True) -> Dict[str, torch.Tensor]:
+    """fp32 tensors for UnifiedWanWithMixedConditionModel's OWN parameters (reference
+    unified_model.py:78-92): vlm_norm, vlm_proj and the VisualContextAdapter."""
+    rng = np.random.default_rng(seed + 101)
+    td, d, cin = cfg["text_dim"], cfg["dim"], cfg["in_dim"]
+    sd = {"vlm_norm.weight": 1.0 + _normal(rng, (vlm_in_dim,), 0.05),
+          "vlm_proj.weight": _xavier(rng, td, vlm_in_dim), "vlm_proj.bias": _normal(rng, (td,), 0.02)}
+    if with_adapter:
+        k = cin * adapter_patch[0] * adapter_patch[1] * adapter_patch[2]
+        sd["visual_context_adapter.patch_embedding.weight"] = _xavier(rng, d, k).view(d, cin, *adapter_patch).contiguous()
+        sd["visual_context_adapter.patch_embedding.bias"] = _normal(rng, (d,), 0.02)
+        sd["visual_context_adapter.projection.weight"] = _xavier(rng, td, d)
+        sd["visual_context_adapter.projection.bias"] = _normal(rng, (td,), 0.02)
+    return sd
+
+
+def unified_inputs(cfg: dict, vlm_in_dim: int, n_vlm, n_text, visual_grid, seed: int = 7,
+                   special_tokens: bool = True):
+    """Per-sample conditions: n_vlm / n_text are lists (None = condition absent for that sample),
+    visual_grid is (F, H, W) of the conditioning latent or None."""
+    rng = np.random.default_rng(seed + 13)
+    B = len(n_text)
+    ar = [None if n is None else _normal(rng, (n, vlm_in_dim), 1.0) for n in n_vlm]
+    ctx = [None if n is None else _normal(rng, (n, cfg["text_dim"]), 1.0) for n in n_text]
+    vis = None if visual_grid is None else [_normal(rng, (cfg["in_dim"], *visual_grid), 1.0) for _ in range(B)]
+    st = None
+    if special_tokens:
+        st = {k: _normal(rng, (1, cfg["text_dim"]), 1.0) for k in ("<img_st>", "<img_ed>", "<prp_st>", "<prp_ed>")}
+    if all(a is None for a in ar):
+        ar = None
+    return ar, ctx, vis, st
