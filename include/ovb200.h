@@ -116,9 +116,18 @@ typedef struct ovb_attn_args {
   int32_t B, H, Lq, Lk;
   const int32_t* k_lens;  /* host, may be NULL */
   float softmax_scale;    /* <=0: 1/sqrt(128) */
+  /* Optional device scratch (16-byte aligned) of ovb_attn_workspace_size() bytes.  With it, the
+   * last partial wave of (256-row q block, head, sample) work items is cut along the keys so that it
+   * fills all SMs, and a combine pass merges the partial softmax results; without it (NULL) every
+   * item is one CTA.  Results agree to bf16 rounding; no_split != 0 forces the one-CTA form. */
+  void* workspace;
+  int64_t workspace_bytes;
+  int32_t no_split;
 } ovb_attn_args;
 
 int ovb_attn_fwd(const ovb_attn_args* args, void* stream);
+/* Upper bound of the scratch ovb_attn_fwd can use for these shapes (0: the launch has no partial wave). */
+int64_t ovb_attn_workspace_size(const ovb_attn_args* args);
 
 /* ---- LayerNorm (+ AdaLN modulation or affine) ------------------------------------------------
  * y = LN_eps(x) * a + b over the last dim (fp32 statistics, two-pass like torch.layer_norm).

@@ -44,6 +44,7 @@ class AttnArgs(C.Structure):
         ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
         ("k_lens", C.POINTER(C.c_int32)),
         ("softmax_scale", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("no_split", C.c_int32),
     ]
 
 
@@ -109,6 +110,7 @@ _SIGNATURES = {
     "ovb_launch_count": (C.c_int64, []),
     "ovb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "ovb_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "ovb_attn_workspace_size": (C.c_int64, [C.POINTER(AttnArgs)]),
     "ovb_layernorm": (C.c_int, [C.POINTER(LnArgs), C.c_void_p]),
     "ovb_rmsnorm_rope": (C.c_int, [C.POINTER(RmsRopeArgs), C.c_void_p]),
     "ovb_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

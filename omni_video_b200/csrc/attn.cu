@@ -54,6 +54,14 @@ struct AttnParams {
   int Lq, Lk, H;
   float scale_log2;  // softmax_scale * log2(e)
   int kl0, kl1, kl2, kl3, kl4, kl5, kl6, kl7;  // per-sample valid keys (B <= 8)
+  // Work decomposition: item = (q block, head, sample), q block fastest (CTAs that run together
+  // share a head's K/V in L2).  CTAs [0, n_whole) take one whole item each; the last, partial wave
+  // of items is cut `parts` ways along the keys so that it fills the machine: CTA n_whole + r
+  // computes keys slice r % parts of item n_whole + r / parts and leaves an UNNORMALISED partial
+  // (O, running max, row sum) in the workspace for attn_combine_kernel.
+  int nqb, n_whole, parts;
+  float* ws_o;   // [n_tail_ctas][256][128] fp32
+  float2* ws_ml; // [n_tail_ctas][256] (max in the log2 domain, row sum)
 };
 
 __device__ __forceinline__ void setmaxnreg_dec_72() {
@@ -86,12 +94,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_blk = blockIdx.x;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
+  int item = blockIdx.x, part = 0, nparts = 1, slot = -1;
+  if (item >= p.n_whole) {
+    slot = item - p.n_whole;
+    item = p.n_whole + slot / p.parts;
+    part = slot % p.parts;
+    nparts = p.parts;
+  }
+  const int q_blk = item % p.nqb;
+  const int head = (item / p.nqb) % p.H;
+  const int batch = item / (p.nqb * p.H);
   const int k_len = batch == 0 ? p.kl0 : batch == 1 ? p.kl1 : batch == 2 ? p.kl2 : batch == 3 ? p.kl3
                   : batch == 4 ? p.kl4 : batch == 5 ? p.kl5 : batch == 6 ? p.kl6 : p.kl7;
-  const int n_kv = (k_len + 127) / 128;
+  const int n_kv_all = (k_len + 127) / 128;
+  const int kv0 = (n_kv_all * part) / nparts;               // first KV tile of this CTA
+  const int n_kv = (n_kv_all * (part + 1)) / nparts - kv0;  // tiles of this CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -136,12 +153,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ph = (j / kKVStages) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_expect_tx(&k_full[s], kTileBytes);
-        tma_load_3d(sK + s * kTileBytes, &tmK, &k_full[s], col, j * 128, batch);
-        tma_load_3d(sK + s * kTileBytes + kBoxBytes, &tmK, &k_full[s], col + 64, j * 128, batch);
+        const int krow = (kv0 + j) * 128;
+        tma_load_3d(sK + s * kTileBytes, &tmK, &k_full[s], col, krow, batch);
+        tma_load_3d(sK + s * kTileBytes + kBoxBytes, &tmK, &k_full[s], col + 64, krow, batch);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_expect_tx(&v_full[s], kTileBytes);
-        tma_load_3d(sV + s * kTileBytes, &tmV, &v_full[s], col, j * 128, batch);
-        tma_load_3d(sV + s * kTileBytes + kBoxBytes, &tmV, &v_full[s], col + 64, j * 128, batch);
+        tma_load_3d(sV + s * kTileBytes, &tmV, &v_full[s], col, krow, batch);
+        tma_load_3d(sV + s * kTileBytes + kBoxBytes, &tmV, &v_full[s], col + 64, krow, batch);
       }
     } else if (warp == 1 && n_kv > 0 && elect_one()) {
       // -------------------------------------------------------- MMA issuer
@@ -275,7 +293,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int t = 0; t < 32; ++t) s[c * 32 + t] = __uint_as_float(r[t]);
       }
-      const int valid = k_len - j * 128;  // kMask: 1..127
+      const int valid = k_len - (kv0 + j) * 128;  // kMask: 1..127
       if constexpr (kMask) {
 #pragma unroll
         for (int t = 0; t < 32; ++t) s[t] = t < valid ? s[t] : -INFINITY;
@@ -402,40 +420,65 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       publish(&p_full[wg]);
       OVB_TRACE(j >= 64 && j < 72 && quad == OVB_TRACE_QUAD && lane == 0, (j - 64) * 32 + 8 + wg * 8 + 4);  // P published
     };
-    const int n_full = k_len >> 7;  // tiles with all 128 keys valid
+    const int n_full = max(0, min(n_kv, (k_len >> 7) - kv0));  // this CTA's tiles with all 128 keys valid
 #pragma unroll 1
     for (int j = 0; j < n_full; ++j) process_tile(j, std::false_type{});
     if (n_full < n_kv) process_tile(n_full, std::true_type{});
 
-    // ---- epilogue: O / l -> bf16 -> global (one 256-byte row segment per thread)
+    // ---- epilogue
     const bool row_ok = q_row < p.Lq;
-    __nv_bfloat16* orow = p.out + static_cast<long long>(batch) * p.o_batch_stride +
-                          static_cast<long long>(q_row) * p.o_row_stride + head * 128;
-    if (n_kv > 0) {
-      mbar_wait(&o_full[wg], 0);
-      tc_fence_after();
-      const float inv_l = 1.0f / l_sum;
+    if (slot >= 0) {
+      // key-split CTA: unnormalised O, running max (log2 domain) and row sum -> workspace
+      const long long prow = static_cast<long long>(slot) * 256 + wg * 128 + quad * 32 + lane;
+      float* wo = p.ws_o + prow * 128;
+      if (n_kv > 0) {
+        mbar_wait(&o_full[wg], 0);
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tO + c * 32, r);
-        tmem_wait_ld();
-        if (row_ok) {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tO + c * 32, r);
+          tmem_wait_ld();
+          if (row_ok) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
-            o.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
-            o.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
-            o.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(wo + c * 32 + g * 4) =
+                  make_uint4(r[g * 4], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]);
           }
         }
       }
-    } else if (row_ok) {
-      const uint4 z = make_uint4(0, 0, 0, 0);
+      // a slice without keys contributes nothing: row sum 0 tells the combine pass to skip it
+      if (row_ok) p.ws_ml[prow] = n_kv > 0 ? make_float2(m_used * scale, l_sum) : make_float2(-INFINITY, 0.f);
+    } else {
+      // O / l -> bf16 -> global (one 256-byte row segment per thread)
+      __nv_bfloat16* orow = p.out + static_cast<long long>(batch) * p.o_batch_stride +
+                            static_cast<long long>(q_row) * p.o_row_stride + head * 128;
+      if (n_kv > 0) {
+        mbar_wait(&o_full[wg], 0);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_sum;
 #pragma unroll
-      for (int g = 0; g < 16; ++g) *reinterpret_cast<uint4*>(orow + g * 8) = z;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tO + c * 32, r);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+              o.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+              o.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+              o.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+            }
+          }
+        }
+      } else if (row_ok) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int g = 0; g < 16; ++g) *reinterpret_cast<uint4*>(orow + g * 8) = z;
+      }
     }
   }
 
@@ -447,6 +490,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// Merges the key-split partials of the last wave (see AttnParams): for every row of every tail item
+//   out = sum_p O_p 2^(m_p - m) / sum_p l_p 2^(m_p - m),   m = max_p m_p   (m in the log2 domain).
+// One thread per 8 output columns; 16 threads per row.
+__global__ void __launch_bounds__(256)
+attn_combine_kernel(const AttnParams p, int n_tail_items) {
+  const int row_in_grid = blockIdx.x * 16 + (threadIdx.x >> 4);
+  const int col = (threadIdx.x & 15) * 8;
+  const int t = row_in_grid >> 8;  // tail item
+  const int r = row_in_grid & 255;
+  if (t >= n_tail_items) return;
+  const int item = p.n_whole + t;
+  const int q_blk = item % p.nqb;
+  const int head = (item / p.nqb) % p.H;
+  const int batch = item / (p.nqb * p.H);
+  const int q_row = q_blk * 256 + r;
+  if (q_row >= p.Lq) return;
+  float m = -INFINITY;
+  for (int k = 0; k < p.parts; ++k) {
+    const float2 ml = p.ws_ml[static_cast<long long>(t * p.parts + k) * 256 + r];
+    if (ml.y > 0.f) m = fmaxf(m, ml.x);
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float l = 0.f;
+  for (int k = 0; k < p.parts; ++k) {
+    const long long prow = static_cast<long long>(t * p.parts + k) * 256 + r;
+    const float2 ml = p.ws_ml[prow];
+    if (!(ml.y > 0.f)) continue;
+    const float w = fast_exp2(ml.x - m);
+    l += ml.y * w;
+    const float4 a = *reinterpret_cast<const float4*>(p.ws_o + prow * 128 + col);
+    const float4 b = *reinterpret_cast<const float4*>(p.ws_o + prow * 128 + col + 4);
+    acc[0] += a.x * w; acc[1] += a.y * w; acc[2] += a.z * w; acc[3] += a.w * w;
+    acc[4] += b.x * w; acc[5] += b.y * w; acc[6] += b.z * w; acc[7] += b.w * w;
+  }
+  const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+  uint4 o;
+  o.x = pack_bf16x2(acc[0] * inv_l, acc[1] * inv_l);
+  o.y = pack_bf16x2(acc[2] * inv_l, acc[3] * inv_l);
+  o.z = pack_bf16x2(acc[4] * inv_l, acc[5] * inv_l);
+  o.w = pack_bf16x2(acc[6] * inv_l, acc[7] * inv_l);
+  __nv_bfloat16* orow = p.out + static_cast<long long>(batch) * p.o_batch_stride +
+                        static_cast<long long>(q_row) * p.o_row_stride + head * 128;
+  *reinterpret_cast<uint4*>(orow + col) = o;
+}
+
 }  // namespace ovb
 
 #ifdef OVB_ATTN_TRACE
@@ -454,6 +542,62 @@ extern "C" int ovb_attn_set_trace(long long* dev_buf) {
   return cudaMemcpyToSymbol(ovb::g_attn_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+namespace ovb {
+
+struct AttnSplit {
+  int n_whole;  // items computed by one CTA each
+  int n_tail;   // items of the last, partial wave, cut `parts` ways along the keys
+  int parts;
+};
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// One CTA per SM (227 KB of shared memory, all 512 TMEM columns), equal-cost items: T items take
+// ceil(T / SMs) rounds.  When the last round is mostly empty, its r items are cut g ways along the
+// keys: ceil(r g / SMs) / g rounds instead of 1.  Only done when a workspace was passed, every
+// slice keeps >= 8 KV tiles, and at least 4 % of the whole launch is saved.
+static AttnSplit plan_split(const ovb_attn_args* a, int min_k_len) {
+  const int nqb = (a->Lq + 255) / 256;
+  const long long T = static_cast<long long>(nqb) * a->H * a->B;
+  const int W = sm_count();
+  AttnSplit sp{static_cast<int>(T), 0, 1};
+  const int r = static_cast<int>(T % W);
+  if (a->workspace == nullptr || r == 0 || a->no_split) return sp;
+  const int n_kv = (min_k_len + 127) / 128;
+  const double whole_rounds = static_cast<double>(T / W);
+  double best = 1.0;
+  int best_g = 1;
+  for (int g = 2; g <= 8 && n_kv / g >= 8; ++g) {
+    const double tail = static_cast<double>((static_cast<long long>(r) * g + W - 1) / W) / g + 0.02 * g;
+    if (tail < best) { best = tail; best_g = g; }
+  }
+  if (best_g == 1 || (1.0 - best) < 0.04 * (whole_rounds + 1.0)) return sp;
+  const long long need = static_cast<long long>(r) * best_g * 256 * (128 * 4 + 8);
+  if (a->workspace_bytes < need) return sp;
+  sp.n_whole = static_cast<int>(T - r);
+  sp.n_tail = r;
+  sp.parts = best_g;
+  return sp;
+}
+
+}  // namespace ovb
+
+extern "C" int64_t ovb_attn_workspace_size(const ovb_attn_args* a) {
+  if (a == nullptr || a->Lq <= 0 || a->H <= 0 || a->B <= 0) return 0;
+  const long long T = static_cast<long long>((a->Lq + 255) / 256) * a->H * a->B;
+  const long long r = T % ovb::sm_count();
+  return r * 8 * 256 * (128 * 4 + 8);  // worst case: 8-way split of the last wave
+}
 
 extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
   using namespace ovb;
@@ -517,15 +661,30 @@ extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
   const float scale = a->softmax_scale > 0.f ? a->softmax_scale : 0.08838834764831845f;
   p.scale_log2 = scale * 1.4426950408889634f;
   int kls[8];
+  int min_kl = a->Lk;
   for (int b = 0; b < 8; ++b) {
     int kl = a->Lk;
     if (a->k_lens != nullptr && b < a->B) kl = a->k_lens[b];
     OVB_CHECK_ARG(kl >= 0 && kl <= a->Lk, "ovb_attn_fwd: k_lens[%d]=%d outside [0, %d]", b, kl,
                   a->Lk);
     kls[b] = kl;
+    if (b < a->B && kl < min_kl) min_kl = kl;
   }
   p.kl0 = kls[0]; p.kl1 = kls[1]; p.kl2 = kls[2]; p.kl3 = kls[3];
   p.kl4 = kls[4]; p.kl5 = kls[5]; p.kl6 = kls[6]; p.kl7 = kls[7];
+
+  const AttnSplit sp = plan_split(a, min_kl);
+  p.nqb = (a->Lq + 255) / 256;
+  p.n_whole = sp.n_whole;
+  p.parts = sp.parts;
+  p.ws_o = nullptr;
+  p.ws_ml = nullptr;
+  if (sp.n_tail > 0) {
+    // workspace layout: [n_tail * parts][256][128] fp32 partial O, then [n_tail * parts][256] float2
+    const long long ctas = static_cast<long long>(sp.n_tail) * sp.parts;
+    p.ws_o = reinterpret_cast<float*>(a->workspace);
+    p.ws_ml = reinterpret_cast<float2*>(p.ws_o + ctas * 256 * 128);
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -533,10 +692,14 @@ extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     attr_set = true;
   }
-  dim3 grid((a->Lq + 255) / 256, a->H, a->B);
-  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK,
-                                                                                        tmV, p);
+  const int grid = sp.n_whole + sp.n_tail * sp.parts;
+  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  if (sp.n_tail > 0) {
+    attn_combine_kernel<<<sp.n_tail * 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, sp.n_tail);
+    OVB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
   return OVB_OK;
 }

@@ -131,11 +131,26 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, epil
 
 
 # ------------------------------------------------------------------------------------- attention
+_attn_ws = {}  # (device index, stream) -> uint8 scratch for the key-split last wave of ovb_attn_fwd
+
+
+def _attn_workspace(lib, args, device):
+    need = int(lib.ovb_attn_workspace_size(C.byref(args)))
+    if need <= 0:
+        return None
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _attn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, device=device, dtype=torch.uint8)
+        _attn_ws[key] = ws
+    return ws
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
               k_lens: Optional[Sequence[int]] = None, softmax_scale: Optional[float] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, split_keys: bool = True) -> torch.Tensor:
     """q: [B, Lq, H, 128], k/v: [B, Lk, H, 128] bf16 views (inner two dims contiguous).
-    Returns bf16 [B, Lq, H, 128]."""
+    Returns bf16 [B, Lq, H, 128].  split_keys=False forces one CTA per (q block, head, sample)."""
     _need_cuda(q, k, v, out)
     lib = _lib.load()
     assert q.dim() == 4 and k.dim() == 4 and v.dim() == 4
@@ -162,6 +177,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
         arr = (C.c_int32 * B)(*kl)
         args.k_lens = C.cast(arr, C.POINTER(C.c_int32))
     args.softmax_scale = float(softmax_scale) if softmax_scale is not None else 0.0
+    args.no_split = 0 if split_keys else 1
+    ws = _attn_workspace(lib, args, q.device) if split_keys else None
+    if ws is not None:
+        args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
     ev = _tl_begin()
     _lib.check(lib.ovb_attn_fwd(C.byref(args), _stream()), "ovb_attn_fwd")
     if ev is not None:

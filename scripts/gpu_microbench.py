@@ -86,6 +86,11 @@ def bench_attn(L, H, Lk, res):
     med, best = time_fn(lambda: ops.attention(q, k, v, out=out), iters=5, warmup=2)
     r = dict(kind="attn", L=L, H=H, Lk=Lk, ovb_ms=med, ovb_tflops=fl / med / 1e9)
     line = f"attn L={L} Lk={Lk} H={H}: ovb {med:.3f} ms {r['ovb_tflops']:.0f} TF/s"
+    items = ((L + 255) // 256) * H
+    if items % 148 and Lk >= 4096:
+        med_w, _ = time_fn(lambda: ops.attention(q, k, v, out=out, split_keys=False), iters=5, warmup=2)
+        r.update(whole_items_ms=med_w, whole_items_tflops=fl / med_w / 1e9)
+        line += f" (one CTA per item: {med_w:.3f} ms {fl / med_w / 1e9:.0f} TF/s; {items} items on 148 SMs)"
     try:
         import flash_attn
         fa = lambda: flash_attn.flash_attn_func(q, k, v)  # noqa: E731
@@ -133,6 +138,8 @@ def main():
     bench_attn(4096, 12, 4096, res)
     bench_attn(L, 12, L, res)
     bench_attn(L, 12, 512, res)
+    bench_attn(L, 3, L, res)    # per-rank shape of cfg2 x ulysses4 on 8 GPUs: 384 items = 2.6 waves
+    bench_attn(L, 6, L, res)    # cfg2 x ulysses2 on 4 GPUs: 768 items = 5.2 waves
     if not quick:
         bench_attn(L, 40, L, res)
     bench_elementwise(L, 1536, res)

@@ -160,6 +160,33 @@ def test_attention_vs_oracle(ops, B, H, Lq, Lk, k_lens):
         assert (out.float().cpu() - ref).abs().max().item() < 0.05, name
 
 
+SPLIT_CASES = [
+    # B, H, Lq, Lk, k_lens: launches whose last wave is cut along the keys (ovb_attn_fwd, AttnSplit)
+    (1, 1, 2560, 8192, None),            # 10 items on 148 SMs -> 7-way key split of every item
+    (1, 1, 2500, 8192, [8100]),          # ragged rows at the end of Lq + a masked last key tile
+    (2, 1, 1280, 4096, [4096, 2100]),    # slices of different length per sample
+    (1, 3, 13056, 4096, None),           # 153 items: one whole wave + 5 tail items
+]
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,k_lens", SPLIT_CASES)
+def test_attention_key_split_last_wave(ops, B, H, Lq, Lk, k_lens):
+    rng = _rng(B * 7 + H * 5 + Lq + Lk)
+    q = _randn(rng, B, Lq, H, 128).to(bf16).cuda()
+    k = _randn(rng, B, Lk, H, 128).to(bf16).cuda()
+    v = _randn(rng, B, Lk, H, 128).to(bf16).cuda()
+    from omni_video_b200 import _lib as L
+    before = L.launch_count()
+    out = ops.attention(q, k, v, k_lens=k_lens)
+    assert L.launch_count() - before == 2, "expected the key-split form (attention + combine launch)"
+    whole = ops.attention(q, k, v, k_lens=k_lens, split_keys=False)
+    ref = _attn_ref_gpu(q, k, v, k_lens)
+    assert O.rel_l2(out.float().cpu(), ref.cpu()) < 8e-3
+    assert (out.float() - ref).abs().max().item() < 0.05
+    # the two decompositions agree to bf16 rounding of the output
+    assert (out.float() - whole.float()).abs().max().item() <= 2 ** -7 * max(1.0, whole.float().abs().max().item())
+
+
 def test_attention_strided_qkv_buffer(ops):
     """q, k, v living inside one fused [L, 3*H*128] projection buffer (how DiTEngine calls it)."""
     rng = _rng(5)

