@@ -123,6 +123,86 @@ __global__ void layernorm_kernel(const LnParams p) {
     store8_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + c0, y);
 }
 
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One WARP per row, the row held in registers (VPL 16-byte vectors per lane, lane i owns vectors
+// i, i+32, ...: every warp-wide access is one contiguous 512 B / 1 KB run).  No shared memory and
+// no __syncthreads: the two reductions are five shuffles each, and 8 independent rows are in
+// flight per CTA.  (The one-CTA-per-row form below spends most of its time in the two block
+// barriers: 0.59 / 0.36 of copy bandwidth for LayerNorm / RMSNorm at d = 1536.)
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * 8;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += warps) {
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c0 = (i * 32 + lane) * 8;
+      if (c0 < p.d) {
+        if (p.x_is_bf16)
+          load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx + c0, v[i]);
+        else
+          load8_f32(reinterpret_cast<const float*>(p.x) + row * p.ldx + c0, v[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+    const float mean = warp_sum(s) / p.d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if ((i * 32 + lane) * 8 < p.d) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = v[i][j] - mean;
+          q += t * t;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / p.d + p.eps);
+    const int sample = row / p.rows_per_sample;
+    const long long mod_off = sample * p.mod_sample_stride + (row - sample * p.rows_per_sample) * p.mod_row_stride;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c0 = (i * 32 + lane) * 8;
+      if (c0 >= p.d) continue;
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[j] = (v[i][j] - mean) * rstd;
+        if (p.round_ln_bf16) y[j] = bf16_round(y[j]);
+      }
+      if (p.mode == OVB_LN_MODULATE) {
+        float sc[8], sh[8];
+        load8_f32(reinterpret_cast<const float*>(p.a) + mod_off + c0, sc);
+        load8_f32(reinterpret_cast<const float*>(p.b) + mod_off + c0, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = y[j] * (1.0f + sc[j]) + sh[j];
+      } else {
+        float w[8], bb[8];
+        load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.a) + c0, w);
+        load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.b) + c0, bb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = y[j] * w[j] + bb[j];
+      }
+      if (p.out_is_f32)
+        store8_f32(reinterpret_cast<float*>(p.out) + row * p.ldo + c0, y);
+      else
+        store8_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + c0, y);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // RMSNorm over full d + RoPE, in place on bf16.  Bytes/element: 2 + 2 = 4.
 struct RmsRopeParams {
@@ -185,6 +265,85 @@ __global__ void rmsnorm_rope_kernel(const RmsRopeParams p) {
     }
   }
   store8_bf16(ptr, y);
+}
+
+// Warp-per-row form of the above (see layernorm_warp_kernel).  This kernel is ISSUE-bound, not
+// HBM-bound, if written naively (~150 instructions per 16-byte vector), so:
+//   * the row stays packed as bf16 in registers between the two passes (4 registers per vector);
+//   * bf16(bf16(x * rinv) * w): the second product is one HMUL2.BF16 per pair — the product of two
+//     bf16 values is exact in fp32, so its bf16 rounding is the reference's (`.type_as(x) * weight`);
+//   * a lane's vectors all sit at the same offset inside a head (vector stride 32 lanes x 8 = 256
+//     columns = 2 heads), so its four (cos, sin) pairs are fetched ONCE per row, not per vector.
+template <int VPL>
+__global__ void __launch_bounds__(256) rmsnorm_rope_warp_kernel(const RmsRopeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * 8;
+  const int hw = p.H * p.W;
+  const int n_tok = p.F * hw;
+  const int pair0 = (lane & 15) * 4;  // ((i*32 + lane) * 8 & 127) / 2 for every i
+  // element offset of each of this lane's vectors inside a row (column-split layout): row-invariant
+  long long off[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c0 = (i * 32 + lane) * 8;
+    const int seg = c0 / p.cols_per_split;
+    off[i] = seg * p.col_split_stride + (c0 - seg * p.cols_per_split);
+  }
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += warps) {
+    uint4 raw[VPL];
+    float q = 0.f;
+    __nv_bfloat16* xrow = p.x + row * p.ldx;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c0 = (i * 32 + lane) * 8;
+      raw[i] = make_uint4(0, 0, 0, 0);
+      if (c0 < p.d) raw[i] = *reinterpret_cast<const uint4*>(xrow + off[i]);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(u[j] << 16), hi = __uint_as_float(u[j] & 0xffff0000u);
+        q = fmaf(lo, lo, q);
+        q = fmaf(hi, hi, q);
+      }
+    }
+    const float rinv = rsqrtf(warp_sum(q) / p.d + p.eps);
+    const int tok = p.token_offset + row % p.rows_per_sample;
+    const bool rotate = p.rope && tok < n_tok;
+    float2 cs[4];
+    if (rotate) {
+      const int f = tok / hw;
+      const int rem = tok - f * hw;
+      const int h_ = rem / p.W;
+      const int w_ = rem - h_ * p.W;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pr = pair0 + j;
+        cs[j] = p.cs[(pr < 22 ? f : (pr < 43 ? h_ : w_)) * 64 + pr];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c0 = (i * 32 + lane) * 8;
+      if (c0 >= p.d) continue;
+      const uint4 wv = *reinterpret_cast<const uint4*>(p.weight + c0);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw[i]);
+      const uint32_t* wu = reinterpret_cast<const uint32_t*>(&wv);
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(u[j] << 16) * rinv, hi = __uint_as_float(u[j] & 0xffff0000u) * rinv;
+        __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+        t = __hmul2(t, *reinterpret_cast<const __nv_bfloat162*>(&wu[j]));
+        uint32_t y = *reinterpret_cast<uint32_t*>(&t);
+        if (rotate) {
+          const float xe = __uint_as_float(y << 16), xo = __uint_as_float(y & 0xffff0000u);
+          y = pack_bf16x2(xe * cs[j].x - xo * cs[j].y, xe * cs[j].y + xo * cs[j].x);
+        }
+        o[j] = y;
+      }
+      *reinterpret_cast<uint4*>(xrow + off[i]) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -380,6 +539,13 @@ __global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ mod,
 
 using namespace ovb;
 
+// grid for the warp-per-row kernels: 8 rows per CTA pass, at most 8 resident CTAs' worth per SM
+static inline int warp_row_grid(int rows) {
+  const long long ctas = (static_cast<long long>(rows) + 7) / 8;
+  const long long cap = 148LL * 8;
+  return static_cast<int>(ctas < cap ? ctas : cap);
+}
+
 static inline int ew_grid(long long work_items, int threads) {
   long long g = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
@@ -406,8 +572,21 @@ extern "C" int ovb_layernorm(const ovb_ln_args* a, void* stream) {
   p.mod_row_stride = a->mod_row_stride; p.mod_sample_stride = a->mod_sample_stride;
   p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->rows;
   p.round_ln_bf16 = a->round_ln_bf16;
-  const int threads = ((a->d / 8 + 31) / 32) * 32;
-  layernorm_kernel<<<a->rows, threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const int vpl = (a->d / 8 + 31) / 32;  // 16-byte vectors per lane with one warp per row
+  const int wgrid = warp_row_grid(a->rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vpl <= 1) layernorm_warp_kernel<1><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 2) layernorm_warp_kernel<2><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 4) layernorm_warp_kernel<4><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 6) layernorm_warp_kernel<6><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 8) layernorm_warp_kernel<8><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 12) layernorm_warp_kernel<12><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 16) layernorm_warp_kernel<16><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 20) layernorm_warp_kernel<20><<<wgrid, 256, 0, st>>>(p);
+  else {  // d > 5120: the row no longer fits one warp's registers in fp32
+    const int threads = ((a->d / 8 + 31) / 32) * 32;
+    layernorm_kernel<<<a->rows, threads, 0, st>>>(p);
+  }
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OVB_OK;
@@ -440,8 +619,20 @@ extern "C" int ovb_rmsnorm_rope(const ovb_rmsnorm_rope_args* a, void* stream) {
   p.token_offset = a->token_offset;
   p.cols_per_split = a->d / col_split;
   p.col_split_stride = col_split > 1 ? a->col_split_stride : 0;
-  const int threads = ((a->d / 8 + 31) / 32) * 32;
-  rmsnorm_rope_kernel<<<a->rows, threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const int vpl = (a->d / 8 + 31) / 32;
+  const int wgrid = warp_row_grid(a->rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vpl <= 1) rmsnorm_rope_warp_kernel<1><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 2) rmsnorm_rope_warp_kernel<2><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 4) rmsnorm_rope_warp_kernel<4><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 6) rmsnorm_rope_warp_kernel<6><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 8) rmsnorm_rope_warp_kernel<8><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 16) rmsnorm_rope_warp_kernel<16><<<wgrid, 256, 0, st>>>(p);
+  else if (vpl <= 20) rmsnorm_rope_warp_kernel<20><<<wgrid, 256, 0, st>>>(p);
+  else {  // d > 5120
+    const int threads = ((a->d / 8 + 31) / 32) * 32;
+    rmsnorm_rope_kernel<<<a->rows, threads, 0, st>>>(p);
+  }
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OVB_OK;
