@@ -123,11 +123,30 @@ typedef struct ovb_attn_args {
   void* workspace;
   int64_t workspace_bytes;
   int32_t no_split;
+  /* Scatter form (B == 1): when out_ptrs is non-NULL it is a HOST array of n_out_ptrs device
+   * pointers and query row r is written to out_ptrs[r / rows_per_out] + (r % rows_per_out) *
+   * o_row_stride + h * 128: the rows of each sequence-parallel rank go straight into that rank's
+   * (peer-mapped) buffer from the kernel's epilogue — the all-to-all after attention
+   * (reference distributed/ulysses.py:54) with no separate collective. */
+  void* const* out_ptrs; int32_t n_out_ptrs; int32_t rows_per_out;
 } ovb_attn_args;
 
 int ovb_attn_fwd(const ovb_attn_args* args, void* stream);
 /* Upper bound of the scratch ovb_attn_fwd can use for these shapes (0: the launch has no partial wave). */
 int64_t ovb_attn_workspace_size(const ovb_attn_args* args);
+
+/* ---- peer transport: cross-GPU signal / wait ---------------------------------------------------
+ * Every rank owns a pad of >= world uint32 flags in memory that all ranks have mapped
+ * (peer_pads[r] = rank r's pad as seen from this process; HOST array of `world` device pointers).
+ * One launch: (1) system-scope fence, so that everything this rank's earlier kernels on `stream`
+ * wrote to peer memory is visible; (2) store `epoch` into slot `rank` of every peer's pad;
+ * (3) wait until all `world` slots of the own pad hold a value >= epoch.  Epochs must increase by one
+ * per call on every rank.  The wait gives up after ~2 s of spinning and sets *status (device uint32,
+ * may be NULL) to 1 instead of hanging the GPU. */
+int ovb_peer_signal_wait(uint32_t* const* peer_pads, int32_t rank, int32_t world, uint32_t epoch,
+                         uint32_t* status, void* stream);
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device ("already enabled" is success). */
+int ovb_enable_peer_access(int32_t peer_device);
 
 /* ---- LayerNorm (+ AdaLN modulation or affine) ------------------------------------------------
  * y = LN_eps(x) * a + b over the last dim (fp32 statistics, two-pass like torch.layer_norm).
@@ -181,6 +200,12 @@ typedef struct ovb_rmsnorm_rope_args {
   int32_t rows_per_sample;
   int32_t token_offset;
   int32_t col_split; int64_t col_split_stride;
+  /* Scatter form (sequence parallelism over peer memory, see "peer transport" below): when dst_ptrs
+   * is non-NULL it is a HOST array of col_split device pointers, and column group g of row r is
+   * written to dst_ptrs[g] + r * dst_ld (+ column inside the group) instead of in place; dst_ptrs[g]
+   * may be memory of another GPU mapped into this process.  copy_only != 0 skips the normalisation
+   * (plain scatter of a column-split matrix, used for V). */
+  void* const* dst_ptrs; int64_t dst_ld; int32_t copy_only;
 } ovb_rmsnorm_rope_args;
 
 int ovb_rmsnorm_rope(const ovb_rmsnorm_rope_args* args, void* stream);

@@ -45,6 +45,7 @@ class AttnArgs(C.Structure):
         ("k_lens", C.POINTER(C.c_int32)),
         ("softmax_scale", C.c_float),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("no_split", C.c_int32),
+        ("out_ptrs", C.POINTER(C.c_void_p)), ("n_out_ptrs", C.c_int32), ("rows_per_out", C.c_int32),
     ]
 
 
@@ -74,6 +75,7 @@ class RmsRopeArgs(C.Structure):
         ("rows_per_sample", C.c_int32),
         ("token_offset", C.c_int32),
         ("col_split", C.c_int32), ("col_split_stride", C.c_int64),
+        ("dst_ptrs", C.POINTER(C.c_void_p)), ("dst_ld", C.c_int64), ("copy_only", C.c_int32),
     ]
 
 
@@ -111,6 +113,9 @@ _SIGNATURES = {
     "ovb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "ovb_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
     "ovb_attn_workspace_size": (C.c_int64, [C.POINTER(AttnArgs)]),
+    "ovb_peer_signal_wait": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p,
+                                       C.c_void_p]),
+    "ovb_enable_peer_access": (C.c_int, [C.c_int32]),
     "ovb_layernorm": (C.c_int, [C.POINTER(LnArgs), C.c_void_p]),
     "ovb_rmsnorm_rope": (C.c_int, [C.POINTER(RmsRopeArgs), C.c_void_p]),
     "ovb_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

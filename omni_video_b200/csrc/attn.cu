@@ -62,7 +62,19 @@ struct AttnParams {
   int nqb, n_whole, parts;
   float* ws_o;   // [n_tail_ctas][256][128] fp32
   float2* ws_ml; // [n_tail_ctas][256] (max in the log2 domain, row sum)
+  // scatter form: row r of the (single) sample goes to outp[r / rows_per_out] (maybe peer memory)
+  __nv_bfloat16* outp[8];
+  int rows_per_out;  // 0: plain form
 };
+
+__device__ __forceinline__ __nv_bfloat16* out_row_ptr(const AttnParams& p, int batch, int q_row, int head) {
+  if (p.rows_per_out > 0) {
+    const int owner = q_row / p.rows_per_out;
+    return p.outp[owner] + static_cast<long long>(q_row - owner * p.rows_per_out) * p.o_row_stride + head * 128;
+  }
+  return p.out + static_cast<long long>(batch) * p.o_batch_stride +
+         static_cast<long long>(q_row) * p.o_row_stride + head * 128;
+}
 
 __device__ __forceinline__ void setmaxnreg_dec_72() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
@@ -451,8 +463,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (row_ok) p.ws_ml[prow] = n_kv > 0 ? make_float2(m_used * scale, l_sum) : make_float2(-INFINITY, 0.f);
     } else {
       // O / l -> bf16 -> global (one 256-byte row segment per thread)
-      __nv_bfloat16* orow = p.out + static_cast<long long>(batch) * p.o_batch_stride +
-                            static_cast<long long>(q_row) * p.o_row_stride + head * 128;
+      __nv_bfloat16* orow = row_ok ? out_row_ptr(p, batch, q_row, head) : nullptr;
       if (n_kv > 0) {
         mbar_wait(&o_full[wg], 0);
         tc_fence_after();
@@ -530,9 +541,7 @@ attn_combine_kernel(const AttnParams p, int n_tail_items) {
   o.y = pack_bf16x2(acc[2] * inv_l, acc[3] * inv_l);
   o.z = pack_bf16x2(acc[4] * inv_l, acc[5] * inv_l);
   o.w = pack_bf16x2(acc[6] * inv_l, acc[7] * inv_l);
-  __nv_bfloat16* orow = p.out + static_cast<long long>(batch) * p.o_batch_stride +
-                        static_cast<long long>(q_row) * p.o_row_stride + head * 128;
-  *reinterpret_cast<uint4*>(orow + col) = o;
+  *reinterpret_cast<uint4*>(out_row_ptr(p, batch, q_row, head) + col) = o;
 }
 
 }  // namespace ovb
@@ -602,7 +611,7 @@ extern "C" int64_t ovb_attn_workspace_size(const ovb_attn_args* a) {
 extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
   using namespace ovb;
   OVB_CHECK_ARG(a != nullptr, "ovb_attn_fwd: null args");
-  OVB_CHECK_ARG(a->q && a->k && a->v && a->out, "ovb_attn_fwd: null q/k/v/out");
+  OVB_CHECK_ARG(a->q && a->k && a->v && (a->out || a->out_ptrs), "ovb_attn_fwd: null q/k/v/out");
   OVB_CHECK_ARG(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0,
                 "ovb_attn_fwd: bad shape B=%d H=%d Lq=%d Lk=%d", a->B, a->H, a->Lq, a->Lk);
   OVB_CHECK_ARG(a->B <= 8, "ovb_attn_fwd: B <= 8 supported (got %d)", a->B);
@@ -673,6 +682,19 @@ extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
   p.kl0 = kls[0]; p.kl1 = kls[1]; p.kl2 = kls[2]; p.kl3 = kls[3];
   p.kl4 = kls[4]; p.kl5 = kls[5]; p.kl6 = kls[6]; p.kl7 = kls[7];
 
+  p.rows_per_out = 0;
+  for (int g = 0; g < 8; ++g) p.outp[g] = nullptr;
+  if (a->out_ptrs != nullptr) {
+    OVB_CHECK_ARG(a->B == 1 && a->rows_per_out > 0 && a->n_out_ptrs >= 1 && a->n_out_ptrs <= 8 &&
+                      static_cast<long long>(a->rows_per_out) * a->n_out_ptrs >= a->Lq,
+                  "ovb_attn_fwd: scatter form needs B == 1 and n_out_ptrs * rows_per_out >= Lq");
+    for (int g = 0; g < a->n_out_ptrs; ++g) {
+      OVB_CHECK_ARG(a->out_ptrs[g] != nullptr && reinterpret_cast<uintptr_t>(a->out_ptrs[g]) % 16 == 0,
+                    "ovb_attn_fwd: out_ptrs[%d] null or misaligned", g);
+      p.outp[g] = reinterpret_cast<__nv_bfloat16*>(a->out_ptrs[g]);
+    }
+    p.rows_per_out = a->rows_per_out;
+  }
   const AttnSplit sp = plan_split(a, min_kl);
   p.nqb = (a->Lq + 255) / 256;
   p.n_whole = sp.n_whole;

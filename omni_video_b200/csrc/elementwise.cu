@@ -216,6 +216,7 @@ struct RmsRopeParams {
   int F, H, W;
   int rows_per_sample, token_offset;
   int cols_per_split; long long col_split_stride;
+  __nv_bfloat16* dst[8]; long long dst_ld; int scatter; int copy_only;  // scatter form (<= 8 column groups)
 };
 
 __global__ void rmsnorm_rope_kernel(const RmsRopeParams p) {
@@ -283,11 +284,13 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_warp_kernel(const RmsRopePar
   const int pair0 = (lane & 15) * 4;  // ((i*32 + lane) * 8 & 127) / 2 for every i
   // element offset of each of this lane's vectors inside a row (column-split layout): row-invariant
   long long off[VPL];
+  __nv_bfloat16* dbase[VPL];  // scatter form: destination of this vector at row 0 (maybe peer memory)
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c0 = (i * 32 + lane) * 8;
     const int seg = c0 / p.cols_per_split;
     off[i] = seg * p.col_split_stride + (c0 - seg * p.cols_per_split);
+    dbase[i] = (p.scatter && c0 < p.d) ? p.dst[seg] + (c0 - seg * p.cols_per_split) : nullptr;
   }
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += warps) {
     uint4 raw[VPL];
@@ -305,6 +308,12 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_warp_kernel(const RmsRopePar
         q = fmaf(lo, lo, q);
         q = fmaf(hi, hi, q);
       }
+    }
+    if (p.copy_only) {  // plain scatter of the row (V): no statistics, no rounding
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if ((i * 32 + lane) * 8 < p.d) *reinterpret_cast<uint4*>(dbase[i] + row * p.dst_ld) = raw[i];
+      continue;
     }
     const float rinv = rsqrtf(warp_sum(q) / p.d + p.eps);
     const int tok = p.token_offset + row % p.rows_per_sample;
@@ -341,7 +350,8 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_warp_kernel(const RmsRopePar
         }
         o[j] = y;
       }
-      *reinterpret_cast<uint4*>(xrow + off[i]) = make_uint4(o[0], o[1], o[2], o[3]);
+      __nv_bfloat16* dptr = p.scatter ? dbase[i] + row * p.dst_ld : xrow + off[i];
+      *reinterpret_cast<uint4*>(dptr) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -619,6 +629,22 @@ extern "C" int ovb_rmsnorm_rope(const ovb_rmsnorm_rope_args* a, void* stream) {
   p.token_offset = a->token_offset;
   p.cols_per_split = a->d / col_split;
   p.col_split_stride = col_split > 1 ? a->col_split_stride : 0;
+  p.scatter = a->dst_ptrs != nullptr;
+  p.copy_only = a->copy_only;
+  p.dst_ld = a->dst_ld;
+  for (int g = 0; g < 8; ++g) p.dst[g] = nullptr;
+  if (p.scatter) {
+    OVB_CHECK_ARG(col_split <= 8 && a->dst_ld % 8 == 0 && a->dst_ld >= a->d / col_split,
+                  "ovb_rmsnorm_rope: scatter form needs col_split <= 8 and dst_ld %% 8 == 0");
+    OVB_CHECK_ARG(a->d / 8 <= 20 * 32, "ovb_rmsnorm_rope: scatter form supports d <= 5120");
+    for (int g = 0; g < col_split; ++g) {
+      OVB_CHECK_ARG(a->dst_ptrs[g] != nullptr && reinterpret_cast<uintptr_t>(a->dst_ptrs[g]) % 16 == 0,
+                    "ovb_rmsnorm_rope: dst_ptrs[%d] null or misaligned", g);
+      p.dst[g] = reinterpret_cast<__nv_bfloat16*>(a->dst_ptrs[g]);
+    }
+  } else {
+    OVB_CHECK_ARG(!a->copy_only, "ovb_rmsnorm_rope: copy_only needs dst_ptrs");
+  }
   const int vpl = (a->d / 8 + 31) / 32;
   const int wgrid = warp_row_grid(a->rows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -829,5 +855,61 @@ extern "C" int ovb_lincomb(const ovb_lincomb_args* a, void* stream) {
   lincomb_kernel<<<ew_grid(a->n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  return OVB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Cross-GPU signal / wait over peer-mapped flag pads (include/ovb200.h "peer transport").
+namespace ovb {
+struct PeerPads { uint32_t* pad[8]; };
+
+__global__ void peer_signal_wait_kernel(const PeerPads pads, int rank, int world, uint32_t epoch,
+                                        uint32_t* status) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(pads.pad[r] + rank), "r"(epoch) : "memory");
+  const uint32_t* mine = pads.pad[rank] + r;
+  const long long t0 = clock64();
+  uint32_t v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died or the epochs diverged
+      if (status != nullptr) *status = 1u;
+      break;
+    }
+  } while (true);
+}
+}  // namespace ovb
+
+extern "C" int ovb_peer_signal_wait(uint32_t* const* peer_pads, int32_t rank, int32_t world,
+                                    uint32_t epoch, uint32_t* status, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(peer_pads != nullptr && world >= 1 && world <= 8 && rank >= 0 && rank < world,
+                "ovb_peer_signal_wait: bad rank/world %d/%d", rank, world);
+  PeerPads pads;
+  for (int r = 0; r < 8; ++r) pads.pad[r] = nullptr;
+  for (int r = 0; r < world; ++r) {
+    OVB_CHECK_ARG(peer_pads[r] != nullptr, "ovb_peer_signal_wait: pad %d is null", r);
+    pads.pad[r] = peer_pads[r];
+  }
+  peer_signal_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pads, rank, world, epoch, status);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_enable_peer_access(int32_t peer_device) {
+  int cur = -1;
+  OVB_CHECK_CUDA(cudaGetDevice(&cur));
+  if (cur == peer_device) return OVB_OK;
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();
+    return OVB_OK;
+  }
+  OVB_CHECK_CUDA(e);
   return OVB_OK;
 }

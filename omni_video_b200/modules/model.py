@@ -353,11 +353,18 @@ class DiTEngine:
         if sp == 1:
             qkv = torch.empty((M, 3 * d), device=dev, dtype=bf16)
         else:
+            from ..distributed import peer
             dg = d // sp
             qkv_send = torch.empty((sp, M, 3 * dg), device=dev, dtype=bf16)
-            qkv_recv = torch.empty((sp, M, 3 * dg), device=dev, dtype=bf16)
-            att_send = torch.empty((sp, M, dg), device=dev, dtype=bf16)
-            att_recv = torch.empty((sp, M, dg), device=dev, dtype=bf16)
+            # peer transport (NVLink stores from the kernels + flag barriers) when the group's memory
+            # can be mapped; otherwise NCCL all_to_all_single on send/receive buffers
+            tr = peer.get_transport(self.sp_group(), dev, M, d)
+            if tr is None:
+                qkv_recv = torch.empty((sp, M, 3 * dg), device=dev, dtype=bf16)
+                att_send = torch.empty((sp, M, dg), device=dev, dtype=bf16)
+                att_recv = torch.empty((sp, M, dg), device=dev, dtype=bf16)
+            else:
+                qkv_recv, att_recv = tr.qkv_recv, tr.att_recv
         grid0 = grids[0]
         if B > 1:
             assert all(g == grid0 for g in grids), "batched samples must share one latent grid"
@@ -387,16 +394,30 @@ class DiTEngine:
                 dg, hg = d // sp, h // sp
                 ops.gemm(hbuf, W.qkv_w, W.qkv_b, epilogue=EPI_BF16, out=qkv_send, n_split=sp)
                 s4 = qkv_send.view(sp, M, 3, dg)
-                ops.rmsnorm_rope_(s4[:, :, 0], W.nq_w, eps, cs_table=self._cs_table, grid=grid0,
-                                  rows_per_sample=s_loc, token_offset=row0)
-                ops.rmsnorm_rope_(s4[:, :, 1], W.nk_w, eps, cs_table=self._cs_table, grid=grid0,
-                                  rows_per_sample=s_loc, token_offset=row0)
-                dist.all_to_all_single(qkv_recv, qkv_send, group=self.sp_group())
+                rope = dict(cs_table=self._cs_table, grid=grid0, rows_per_sample=s_loc, token_offset=row0)
+                if tr is None:
+                    ops.rmsnorm_rope_(s4[:, :, 0], W.nq_w, eps, **rope)
+                    ops.rmsnorm_rope_(s4[:, :, 1], W.nk_w, eps, **rope)
+                    dist.all_to_all_single(qkv_recv, qkv_send, group=self.sp_group())
+                else:
+                    # each rank's head group goes from the normalising kernel straight into that
+                    # rank's receive buffer; V is a plain scatter
+                    ops.rmsnorm_rope_(s4[:, :, 0], W.nq_w, eps, dst_ptrs=tr.q_k_v_dst(0), dst_ld=3 * dg, **rope)
+                    ops.rmsnorm_rope_(s4[:, :, 1], W.nk_w, eps, dst_ptrs=tr.q_k_v_dst(1), dst_ld=3 * dg, **rope)
+                    ops.rmsnorm_rope_(s4[:, :, 2], W.nq_w, eps, dst_ptrs=tr.q_k_v_dst(2), dst_ld=3 * dg,
+                                      copy_only=True)
+                    tr.barrier()
                 # [sp(src rank = token chunk), s_loc, 3, hg, 128] == [seq_len, 3, hg, 128]
                 r5 = qkv_recv.view(1, sp * s_loc, 3, hg, 128)
-                ops.attention(r5[:, :, 0], r5[:, :, 1], r5[:, :, 2], k_lens=seq_lens,
-                              out=att_send.view(1, sp * s_loc, hg, 128))
-                dist.all_to_all_single(att_recv, att_send, group=self.sp_group())
+                if tr is None:
+                    ops.attention(r5[:, :, 0], r5[:, :, 1], r5[:, :, 2], k_lens=seq_lens,
+                                  out=att_send.view(1, sp * s_loc, hg, 128))
+                    dist.all_to_all_single(att_recv, att_send, group=self.sp_group())
+                else:
+                    # the epilogue stores every query row into the buffer of the rank that owns it
+                    ops.attention(r5[:, :, 0], r5[:, :, 1], r5[:, :, 2], k_lens=seq_lens,
+                                  out_ptrs=tr.att_dst, rows_per_out=s_loc, out_row_stride=dg)
+                    tr.barrier()
                 ops.gemm(att_recv, W.o_w, W.o_b, epilogue=EPI_GATE_RESID_F32, out=xres, resid=xres,
                          gate=mb[:, 2], rows_per_sample=s_loc, k_split=sp)
             # ---------------- cross attention (context K/V replicated on every rank: no collective)

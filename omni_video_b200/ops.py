@@ -148,9 +148,13 @@ def _attn_workspace(lib, args, device):
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
               k_lens: Optional[Sequence[int]] = None, softmax_scale: Optional[float] = None,
-              out: Optional[torch.Tensor] = None, split_keys: bool = True) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, split_keys: bool = True,
+              out_ptrs: Optional[Sequence[int]] = None, rows_per_out: int = 0,
+              out_row_stride: int = 0) -> Optional[torch.Tensor]:
     """q: [B, Lq, H, 128], k/v: [B, Lk, H, 128] bf16 views (inner two dims contiguous).
-    Returns bf16 [B, Lq, H, 128].  split_keys=False forces one CTA per (q block, head, sample)."""
+    Returns bf16 [B, Lq, H, 128].  split_keys=False forces one CTA per (q block, head, sample).
+    Scatter form (B == 1): out_ptrs = raw device pointers (possibly peer-mapped); query row r goes to
+    out_ptrs[r // rows_per_out] + (r % rows_per_out) * out_row_stride + head * 128; returns None."""
     _need_cuda(q, k, v, out)
     lib = _lib.load()
     assert q.dim() == 4 and k.dim() == 4 and v.dim() == 4
@@ -162,14 +166,22 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         assert t.dtype == bf16, f"{n} must be bf16"
         assert t.stride(3) == 1 and t.stride(2) == D, f"{n}: heads must be packed [H,128] per row"
-    if out is None:
-        out = torch.empty((B, Lq, H, D), device=q.device, dtype=bf16)
-    assert out.dtype == bf16 and out.shape == (B, Lq, H, D) and out.stride(3) == 1 and out.stride(2) == D
     args = _lib.AttnArgs()
+    if out_ptrs is not None:
+        assert B == 1 and rows_per_out > 0 and out_row_stride >= H * D and out is None
+        keep = _ptr_array(out_ptrs)
+        args.out_ptrs, args.n_out_ptrs, args.rows_per_out = keep, len(out_ptrs), rows_per_out
+    else:
+        if out is None:
+            out = torch.empty((B, Lq, H, D), device=q.device, dtype=bf16)
+        assert out.dtype == bf16 and out.shape == (B, Lq, H, D) and out.stride(3) == 1 and out.stride(2) == D
     args.q, args.q_row_stride, args.q_batch_stride = q.data_ptr(), q.stride(1), q.stride(0)
     args.k, args.k_row_stride, args.k_batch_stride = k.data_ptr(), k.stride(1), k.stride(0)
     args.v, args.v_row_stride, args.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
-    args.out, args.o_row_stride, args.o_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    if out_ptrs is None:
+        args.out, args.o_row_stride, args.o_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    else:
+        args.out, args.o_row_stride, args.o_batch_stride = None, out_row_stride, 0
     args.B, args.H, args.Lq, args.Lk = B, H, Lq, Lk
     if k_lens is not None:
         kl = [int(x) for x in k_lens]
@@ -238,11 +250,19 @@ def _layernorm(x, mode, a, b, eps, rows_per_sample, out_dtype, round_ln_bf16, ou
 
 
 # ------------------------------------------------------------------------------- rmsnorm (+rope)
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[int(v) for v in ptrs])
+
+
 def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, eps: float, *,
                   cs_table: Optional[torch.Tensor] = None, grid=None, rows_per_sample: int = 0,
-                  token_offset: int = 0) -> torch.Tensor:
+                  token_offset: int = 0, dst_ptrs: Optional[Sequence[int]] = None, dst_ld: int = 0,
+                  copy_only: bool = False) -> torch.Tensor:
     """In place on x: bf16 [rows, d] (ld arbitrary) or [col_split, rows, d/col_split].
-    With cs_table (fp32 [T, 64, 2]) and grid=(F, H, W) also applies the 3-D RoPE."""
+    With cs_table (fp32 [T, 64, 2]) and grid=(F, H, W) also applies the 3-D RoPE.
+    Scatter form: dst_ptrs = col_split raw device pointers (possibly peer-mapped memory of other
+    GPUs); column group g of row r is written to dst_ptrs[g] + r * dst_ld instead of in place;
+    copy_only skips the normalisation (plain scatter)."""
     _need_cuda(x, weight, cs_table)
     lib = _lib.load()
     assert x.dtype == bf16 and weight.dtype == bf16 and weight.is_contiguous()
@@ -266,8 +286,21 @@ def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, eps: float, *,
         args.F, args.H, args.W = F, H, W
         args.rows_per_sample = rows_per_sample or rows
         args.token_offset = token_offset
+    if dst_ptrs is not None:
+        assert len(dst_ptrs) == args.col_split
+        keep = _ptr_array(dst_ptrs)
+        args.dst_ptrs, args.dst_ld, args.copy_only = keep, dst_ld, int(copy_only)
     _lib.check(lib.ovb_rmsnorm_rope(C.byref(args), _stream()), "ovb_rmsnorm_rope")
     return x
+
+
+def peer_signal_wait(pad_ptrs: Sequence[int], rank: int, epoch: int, status: Optional[torch.Tensor] = None):
+    """Cross-GPU barrier on peer-mapped flag pads (include/ovb200.h "peer transport"): makes this rank's
+    earlier peer stores visible, signals every peer with `epoch`, waits for all peers' `epoch`."""
+    lib = _lib.load()
+    _lib.check(lib.ovb_peer_signal_wait(_ptr_array(pad_ptrs), rank, len(pad_ptrs), epoch,
+                                        _ptr(status) if status is not None else None, _stream()),
+               "ovb_peer_signal_wait")
 
 
 # ----------------------------------------------------------------------------- patchify & friends

@@ -53,8 +53,21 @@ def main():
 
     g = init_sequence_parallel_group(world)
     model.sp_group = g
-    out_engine = model(x, t=t, context=ctx, seq_len=seq_len)[0]
+    # (b1) peer transport: kernels store into the peers' buffers, flag barriers (distributed/peer.py)
+    from omni_video_b200.distributed import peer
+    os.environ["OVB_SP_TRANSPORT"] = "peer"
+    for _ in range(3):                                                     # epochs advance, buffers are reused
+        out_engine = model(x, t=t, context=ctx, seq_len=seq_len)[0]
+    tr = next((v for v in peer._transports.values() if v), None)
+    backend = tr.backend if tr else "unavailable -> NCCL"
+    if tr:
+        tr.check()
     e1 = rel_l2(out_engine, ref)
+    # (b2) NCCL all-to-all transport: must give the same bits
+    os.environ["OVB_SP_TRANSPORT"] = "nccl"
+    out_nccl = model(x, t=t, context=ctx, seq_len=seq_len)[0]
+    same = bool(torch.equal(out_nccl, out_engine))
+    os.environ["OVB_SP_TRANSPORT"] = "peer"
 
     for blk in model.blocks:
         blk.self_attn.sp_group = g
@@ -65,9 +78,9 @@ def main():
     out_hooks = model(x, t=t, context=ctx, seq_len=seq_len)[0]
     e2 = rel_l2(out_hooks, ref)
     torch.cuda.synchronize()
-    print(f"[rank {rank}/{world}] ulysses engine vs single-GPU rel-L2 {e1:.3e}; reference-style hooks {e2:.3e}",
-          flush=True)
-    ok = e1 <= 2e-3 and e2 <= 5e-3 and bool(torch.isfinite(out_engine).all())
+    print(f"[rank {rank}/{world}] ulysses engine ({backend}) vs single-GPU rel-L2 {e1:.3e}; peer == nccl bits: {same}; "
+          f"reference-style hooks {e2:.3e}", flush=True)
+    ok = e1 <= 2e-3 and e2 <= 5e-3 and same and bool(torch.isfinite(out_engine).all())
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.destroy_process_group()
