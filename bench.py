@@ -254,6 +254,8 @@ def run_ours(args):
     init_random_(model, 1818)
     if sp_group is not None and sp > 1:
         model.sp_group = sp_group
+    use_graph = (world > 1) if args.graph is None else bool(args.graph)
+    model.use_cuda_graph = use_graph
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1818)
@@ -284,7 +286,9 @@ def run_ours(args):
     for i in range(args.warmup):
         latent = stepper.step(latent, ctx_c, ctx_u, i)
     barrier()
-    ops.timeline = []
+    # per-launch CUDA events (roofline leg) need individual launches: in graph mode they are taken
+    # on one extra eager step right after the timed region instead of inside it
+    ops.timeline = None if use_graph else []
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -297,6 +301,14 @@ def run_ours(args):
     torch.cuda.cudart().cudaProfilerStop()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - n0
+    timeline_steps = args.steps
+    if use_graph:
+        model.use_cuda_graph = False
+        ops.timeline = []
+        latent = stepper.step(latent, ctx_c, ctx_u, args.warmup + args.steps)
+        barrier()
+        model.use_cuda_graph = True
+        timeline_steps = 1
     timeline, ops.timeline = ops.timeline, None
     clk = clocks.stop() if clocks is not None else None
     finite = bool(torch.isfinite(latent).all().item())
@@ -365,10 +377,12 @@ def run_ours(args):
                     peak_source=peaks["source"],
                     launches=agg.get("attn", [0, 0, 0])[2],
                     ms_per_launch=round(agg["attn"][1] / max(1, agg["attn"][2]), 4) if "attn" in agg else None,
-                    share_of_step=round(agg["attn"][1] / dev_ms, 4) if "attn" in agg else None,
+                    share_of_step=round(agg["attn"][1] / (dev_ms * timeline_steps / args.steps), 4) if "attn" in agg else None,
+                    timed_from=("one extra eager step after the timed region (the timed steps replay a CUDA graph)"
+                                if use_graph else "CUDA events around every launch inside the timed region"),
                     gemm_kernel=dict(achieved=round(gemm_tf, 1), frac=round(gemm_tf / peaks["tflops"], 4),
                                      launches=agg.get("gemm", [0, 0, 0])[2],
-                                     share_of_step=round(agg["gemm"][1] / dev_ms, 4) if "gemm" in agg else None),
+                                     share_of_step=round(agg["gemm"][1] / (dev_ms * timeline_steps / args.steps), 4) if "gemm" in agg else None),
                     whole_step=dict(achieved=round(whole_tf / world, 1),
                                     frac=round(whole_tf / world / peaks["tflops"], 4),
                                     tflop_per_step=round(2.0 * fl["total"] / 1e12, 1)))
@@ -384,7 +398,8 @@ def run_ours(args):
                 config=dict(workload=f"OmniVideo2-{args.model} DiT, {args.video} "
                                      f"(latent 16x{Fr}x{H}x{W}, {L} tokens), text_len {args.text_len}, "
                                      "step = cond+uncond forward + CFG + UniPC update, random-init weights",
-                            cfg_batched=bool(stepper.batch_cfg),
+                            cfg_batched=bool(stepper.batch_cfg), cuda_graph=bool(use_graph),
+                            sp_transport=(os.environ.get("OVB_SP_TRANSPORT", "peer") if sp > 1 else None),
                             parallelism=(f"ulysses{sp}" + (f"xcfg{cfg_par}" if cfg_par > 1 else "")) if world > 1 else "single",
                             l2="inputs+weights per step (>2.8 GB) exceed the 126 MB L2; no flush needed",
                             forwards_per_s=round(2 * steps_per_s, 5), finite=finite),
@@ -560,6 +575,10 @@ def main():
                     help="N>1: put the cond/uncond forwards on two Ulysses groups of N/2 ranks even when "
                          "the head count would allow one group of N (what N=8 does for 12 heads)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--graph", dest="graph", action="store_true", default=None,
+                    help="replay the DiT forward as a CUDA graph (default: on for N > 1, where kernels are "
+                         "short enough for launch gaps to matter; off at N = 1)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

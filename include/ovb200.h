@@ -40,6 +40,8 @@ const char* ovb_last_error(void);
 int ovb_check_device(void);
 /* Number of kernels this library has launched from the calling process (bench `gpu_launches`). */
 int64_t ovb_launch_count(void);
+/* Adds n to that counter: for callers that replay a captured CUDA graph of this library's launches. */
+void ovb_add_launch_count(int64_t n);
 
 /* ---- GEMM (tcgen05 / TMEM / TMA) ------------------------------------------------------------
  * out = epilogue( A[M,K] * W[N,K]^T + bias[N] )       bf16 operands, fp32 accumulation in TMEM.
@@ -141,10 +143,12 @@ int64_t ovb_attn_workspace_size(const ovb_attn_args* args);
  * One launch: (1) system-scope fence, so that everything this rank's earlier kernels on `stream`
  * wrote to peer memory is visible; (2) store `epoch` into slot `rank` of every peer's pad;
  * (3) wait until all `world` slots of the own pad hold a value >= epoch.  Epochs must increase by one
- * per call on every rank.  The wait gives up after ~2 s of spinning and sets *status (device uint32,
- * may be NULL) to 1 instead of hanging the GPU. */
+ * per call on every rank: with epoch_counter (device uint32, owned by this rank) the kernel uses
+ * *epoch_counter + 1 and stores it back, which keeps the launch valid inside a replayed CUDA graph;
+ * with epoch_counter == NULL the `epoch` argument is used.  The wait gives up after ~2 s of spinning
+ * and sets *status (device uint32, may be NULL) to 1 instead of hanging the GPU. */
 int ovb_peer_signal_wait(uint32_t* const* peer_pads, int32_t rank, int32_t world, uint32_t epoch,
-                         uint32_t* status, void* stream);
+                         uint32_t* epoch_counter, uint32_t* status, void* stream);
 /* cudaDeviceEnablePeerAccess(peer_device) for the current device ("already enabled" is success). */
 int ovb_enable_peer_access(int32_t peer_device);
 

@@ -110,11 +110,12 @@ _SIGNATURES = {
     "ovb_last_error": (C.c_char_p, []),
     "ovb_check_device": (C.c_int, []),
     "ovb_launch_count": (C.c_int64, []),
+    "ovb_add_launch_count": (None, [C.c_int64]),
     "ovb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "ovb_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
     "ovb_attn_workspace_size": (C.c_int64, [C.POINTER(AttnArgs)]),
     "ovb_peer_signal_wait": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p,
-                                       C.c_void_p]),
+                                       C.c_void_p, C.c_void_p]),
     "ovb_enable_peer_access": (C.c_int, [C.c_int32]),
     "ovb_layernorm": (C.c_int, [C.POINTER(LnArgs), C.c_void_p]),
     "ovb_rmsnorm_rope": (C.c_int, [C.POINTER(RmsRopeArgs), C.c_void_p]),

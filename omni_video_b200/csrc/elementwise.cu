@@ -864,28 +864,36 @@ extern "C" int ovb_lincomb(const ovb_lincomb_args* a, void* stream) {
 namespace ovb {
 struct PeerPads { uint32_t* pad[8]; };
 
-__global__ void peer_signal_wait_kernel(const PeerPads pads, int rank, int world, uint32_t epoch,
-                                        uint32_t* status) {
+__global__ void peer_signal_wait_kernel(const PeerPads pads, int rank, int world, uint32_t epoch_arg,
+                                        uint32_t* epoch_ctr, uint32_t* status) {
   const int r = threadIdx.x;
-  if (r >= world) return;
-  __threadfence_system();
-  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(pads.pad[r] + rank), "r"(epoch) : "memory");
-  const uint32_t* mine = pads.pad[rank] + r;
-  const long long t0 = clock64();
-  uint32_t v;
-  do {
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
-    if (v >= epoch) break;
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died or the epochs diverged
-      if (status != nullptr) *status = 1u;
-      break;
-    }
-  } while (true);
+  // The epoch normally lives in device memory and advances by one per launch, so that the launch
+  // can sit inside a replayed CUDA graph; epoch_arg is used when no counter is given.
+  const uint32_t epoch = epoch_ctr != nullptr ? *epoch_ctr + 1u : epoch_arg;
+  __syncwarp();
+  if (r < world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(pads.pad[r] + rank), "r"(epoch) : "memory");
+    const uint32_t* mine = pads.pad[rank] + r;
+    const long long t0 = clock64();
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died or the epochs diverged
+        if (status != nullptr) *status = 1u;
+        break;
+      }
+    } while (true);
+  }
+  __syncwarp();
+  if (r == 0 && epoch_ctr != nullptr) *epoch_ctr = epoch;
 }
 }  // namespace ovb
 
 extern "C" int ovb_peer_signal_wait(uint32_t* const* peer_pads, int32_t rank, int32_t world,
-                                    uint32_t epoch, uint32_t* status, void* stream) {
+                                    uint32_t epoch, uint32_t* epoch_counter, uint32_t* status,
+                                    void* stream) {
   using namespace ovb;
   OVB_CHECK_ARG(peer_pads != nullptr && world >= 1 && world <= 8 && rank >= 0 && rank < world,
                 "ovb_peer_signal_wait: bad rank/world %d/%d", rank, world);
@@ -895,7 +903,8 @@ extern "C" int ovb_peer_signal_wait(uint32_t* const* peer_pads, int32_t rank, in
     OVB_CHECK_ARG(peer_pads[r] != nullptr, "ovb_peer_signal_wait: pad %d is null", r);
     pads.pad[r] = peer_pads[r];
   }
-  peer_signal_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pads, rank, world, epoch, status);
+  peer_signal_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pads, rank, world, epoch,
+                                                                           epoch_counter, status);
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OVB_OK;

@@ -146,6 +146,7 @@ extern "C" int ovb_abi_version(void) { return OVB_ABI_VERSION; }
 extern "C" const char* ovb_last_error(void) { return ovb::g_last_error; }
 
 extern "C" int64_t ovb_launch_count(void) { return ovb::g_launches.load(); }
+extern "C" void ovb_add_launch_count(int64_t n) { ovb::g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int ovb_check_device(void) {
   int dev = 0;

@@ -117,8 +117,7 @@ class UlyssesPeerTransport:
         self.qkv_dst = [p + me * rows * 3 * dg * 2 for p in self._sym.ptrs]
         self.att_dst = [p + qkv_bytes + me * rows * dg * 2 for p in self._sym.ptrs]
         self.pad_ptrs = [p + pad_off for p in self._sym.ptrs]
-        self.status = torch.zeros(1, device=device, dtype=torch.int32)
-        self.epoch = 0
+        self.state = torch.zeros(2, device=device, dtype=torch.int32)   # (epoch counter, time-out status)
         torch.cuda.synchronize(device)
         dist.barrier(group=group)            # pads are zero everywhere before the first signal
 
@@ -127,12 +126,11 @@ class UlyssesPeerTransport:
         return [p + which * self.dg * 2 for p in self.qkv_dst]
 
     def barrier(self):
-        self.epoch += 1
-        ops.peer_signal_wait(self.pad_ptrs, self.rank, self.epoch, self.status)
+        ops.peer_signal_wait(self.pad_ptrs, self.rank, self.state)
 
     def check(self):
         """Raise if any barrier timed out (call outside the timed region: it synchronises)."""
-        if int(self.status.item()) != 0:
+        if int(self.state[1].item()) != 0:
             raise RuntimeError("peer barrier timed out: a rank of the sequence-parallel group fell behind or died")
 
 

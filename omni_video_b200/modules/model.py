@@ -27,6 +27,7 @@ weights.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -171,6 +172,8 @@ class DiTEngine:
         self._packed = None
         self._packed_key = None
         self._cs_table = None
+        self._graphs = {}           # forward signature -> _GraphedForward
+        self.graph_replays = 0
 
     # -------------------------------------------------------------------------------- weights
     def _key(self):
@@ -316,9 +319,37 @@ class DiTEngine:
                        P.text_w2, P.text_b2, epilogue=EPI_BF16)                     # [B*Lc, d]
         return xres, e, e0, ctx, grids, seq_lens
 
+    # ------------------------------------------------------------------------------ CUDA graph
+    def use_graph(self) -> bool:
+        v = getattr(self.m, "use_cuda_graph", None)
+        return bool(v) if v is not None else os.environ.get("OVB_CUDA_GRAPH", "0") == "1"
+
     @torch.no_grad()
     def forward(self, x: List[torch.Tensor], t: torch.Tensor, context: List[torch.Tensor],
                 seq_len: int, y: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """Eager launch sequence, or — `model.use_cuda_graph = True` / OVB_CUDA_GRAPH=1 — one CUDA graph
+        per forward signature (shapes, context lengths, seq_len): the ~900 launches of a 30-block
+        forward are captured once (all buffers come from the graph's private pool, the peer barriers
+        keep their epoch in device memory) and every later call is input copies + one graph launch.
+        What that buys is the launch gaps: nothing at 32760 tokens on one GPU, several per cent when
+        sequence parallelism cuts every kernel to a fraction of a millisecond."""
+        if (not self.use_graph() or not x[0].is_cuda or t.dim() != 1 or ops.timeline_active()
+                or torch.cuda.is_current_stream_capturing()):
+            return self._forward(x, t, context, seq_len, y)
+        sig = (tuple((tuple(u.shape), u.dtype) for u in x), tuple(t.shape), t.dtype,
+               tuple((tuple(c.shape), c.dtype) for c in context), seq_len,
+               None if y is None else tuple((tuple(u.shape), u.dtype) for u in y), self._key())
+        g = self._graphs.get(sig)
+        if g is None:
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._graphs[sig] = _GraphedForward(self, x, t, context, seq_len, y)
+        self.graph_replays += 1
+        return g(x, t, context, y)
+
+    @torch.no_grad()
+    def _forward(self, x: List[torch.Tensor], t: torch.Tensor, context: List[torch.Tensor],
+                 seq_len: int, y: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
         m = self.m
         if m.model_type == "i2v":
             assert y is not None
@@ -334,7 +365,7 @@ class DiTEngine:
             # :480-481); run samples one after another under sequence parallelism
             out = []
             for i in range(B):
-                out += self.forward([x[i]], t[i:i + 1], [context[i]], seq_len, None)
+                out += self._forward([x[i]], t[i:i + 1], [context[i]], seq_len, None)
             return out
         xres, e, e0, ctx, grids, seq_lens = self.embed(x, t, context, seq_len, sp, rank)
         s_loc = seq_len // sp
@@ -453,6 +484,48 @@ class DiTEngine:
         for b in range(B):
             outs.append(ops.unpatchify(yout[b * seq_len:(b + 1) * seq_len], m.out_dim, grids[b]))
         return outs
+
+
+class _GraphedForward:
+    """One captured DiT forward: static input buffers, a CUDA graph, static outputs."""
+
+    def __init__(self, eng: DiTEngine, x, t, context, seq_len, y):
+        dev = x[0].device
+        self.x = [u.detach().clone() for u in x]
+        self.t = t.detach().to(dev).clone()
+        self.ctx = [c.detach().to(dev).clone() for c in context]
+        self.y = None if y is None else [u.detach().clone() for u in y]
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up: weight packing, workspaces, peer rendezvous
+            for _ in range(2):
+                eng._forward(self.x, self.t, self.ctx, seq_len, self.y)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        n0 = _lib_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = eng._forward(self.x, self.t, self.ctx, seq_len, self.y)
+        self.launches = _lib_launch_count() - n0   # kernels of this library inside one replay
+
+    def __call__(self, x, t, context, y):
+        for dst, src in zip(self.x, x):
+            dst.copy_(src, non_blocking=True)
+        self.t.copy_(t, non_blocking=True)
+        for dst, src in zip(self.ctx, context):
+            dst.copy_(src, non_blocking=True)
+        if y is not None:
+            for dst, src in zip(self.y, y):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        ops.add_launch_count(self.launches)
+        return [o.clone() for o in self.out]
+
+
+def _lib_launch_count() -> int:
+    from .. import _lib
+    return _lib.launch_count()
 
 
 # ------------------------------------------------------------------------------------------------

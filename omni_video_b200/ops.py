@@ -27,6 +27,16 @@ def _stream():
 timeline = None
 
 
+def timeline_active() -> bool:
+    return timeline is not None
+
+
+def add_launch_count(n: int):
+    """Account for kernels of this library launched by a CUDA-graph replay (they do not pass through
+    the C entry points that ovb_launch_count() counts)."""
+    _lib.load().ovb_add_launch_count(int(n))
+
+
 def _tl_begin():
     if timeline is None:
         return None
@@ -294,12 +304,15 @@ def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, eps: float, *,
     return x
 
 
-def peer_signal_wait(pad_ptrs: Sequence[int], rank: int, epoch: int, status: Optional[torch.Tensor] = None):
+def peer_signal_wait(pad_ptrs: Sequence[int], rank: int, state: torch.Tensor):
     """Cross-GPU barrier on peer-mapped flag pads (include/ovb200.h "peer transport"): makes this rank's
-    earlier peer stores visible, signals every peer with `epoch`, waits for all peers' `epoch`."""
+    earlier peer stores visible, signals every peer with the next epoch, waits for all peers' signal.
+    state: int32 [2] on this device = (epoch counter, time-out status), both advanced by the kernel."""
     lib = _lib.load()
-    _lib.check(lib.ovb_peer_signal_wait(_ptr_array(pad_ptrs), rank, len(pad_ptrs), epoch,
-                                        _ptr(status) if status is not None else None, _stream()),
+    assert state.dtype == torch.int32 and state.numel() == 2 and state.is_cuda
+    _lib.check(lib.ovb_peer_signal_wait(_ptr_array(pad_ptrs), rank, len(pad_ptrs), 0,
+                                        C.c_void_p(state.data_ptr()), C.c_void_p(state.data_ptr() + 4),
+                                        _stream()),
                "ovb_peer_signal_wait")
 
 

@@ -129,3 +129,31 @@ def test_ulysses_two_gpus_matches_single_gpu():
                         os.path.join(root, "scripts", "sp_check.py")], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cuda_graph_forward_matches_eager_bit_for_bit():
+    """model.use_cuda_graph: the captured forward replays with new inputs and gives the eager bits;
+    a different context length is a different signature (second graph); launches are accounted."""
+    from omni_video_b200 import _lib
+    from omni_video_b200.modules.model import WanModel
+    cfg = dict(synth.TINY_DIT)
+    sd = synth.dit_state_dict(cfg, seed=1818)
+    with torch.device("cuda"):
+        m = WanModel(**cfg)
+    m.load_state_dict({k: v.cuda() for k, v in sd.items()})
+    m = m.to(torch.bfloat16).eval().requires_grad_(False)
+    cases = []
+    for seed, ctx_len, tval in ((1, 20, 999), (2, 20, 500), (3, 11, 17), (4, 20, 250)):
+        xs, t, ctx = synth.dit_inputs(cfg, (3, 8, 12), ctx_len, seed=seed, timestep=tval)
+        cases.append(([x.cuda() for x in xs], t.cuda(), [c.cuda().to(torch.bfloat16) for c in ctx]))
+    eager = [m(x, t=t, context=c, seq_len=72)[0] for x, t, c in cases]
+    m.use_cuda_graph = True
+    n0 = _lib.launch_count()
+    graphed = [m(x, t=t, context=c, seq_len=72)[0] for x, t, c in cases]
+    per_forward = (_lib.launch_count() - n0)
+    eng = m._engine if hasattr(m, "_engine") else None
+    for a, b in zip(eager, graphed):
+        assert torch.equal(a, b)
+    assert per_forward > 0
+    if eng is not None:
+        assert len(eng._graphs) == 2 and eng.graph_replays == 4
