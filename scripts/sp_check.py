@@ -63,6 +63,14 @@ def main():
     if tr:
         tr.check()
     e1 = rel_l2(out_engine, ref)
+    # (b1') the same through a captured CUDA graph (peer barriers keep their epoch on the device)
+    model.use_cuda_graph = True
+    for _ in range(3):
+        out_graph = model(x, t=t, context=ctx, seq_len=seq_len)[0]
+    model.use_cuda_graph = False
+    graph_same = bool(torch.equal(out_graph, out_engine))
+    if tr:
+        tr.check()
     # (b2) NCCL all-to-all transport: must give the same bits
     os.environ["OVB_SP_TRANSPORT"] = "nccl"
     out_nccl = model(x, t=t, context=ctx, seq_len=seq_len)[0]
@@ -78,9 +86,9 @@ def main():
     out_hooks = model(x, t=t, context=ctx, seq_len=seq_len)[0]
     e2 = rel_l2(out_hooks, ref)
     torch.cuda.synchronize()
-    print(f"[rank {rank}/{world}] ulysses engine ({backend}) vs single-GPU rel-L2 {e1:.3e}; peer == nccl bits: {same}; "
+    print(f"[rank {rank}/{world}] ulysses engine ({backend}) vs single-GPU rel-L2 {e1:.3e}; peer == nccl bits: {same}; graph == eager bits: {graph_same}; "
           f"reference-style hooks {e2:.3e}", flush=True)
-    ok = e1 <= 2e-3 and e2 <= 5e-3 and same and bool(torch.isfinite(out_engine).all())
+    ok = e1 <= 2e-3 and e2 <= 5e-3 and same and graph_same and bool(torch.isfinite(out_engine).all())
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.destroy_process_group()
