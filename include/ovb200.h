@@ -136,6 +136,10 @@ typedef struct ovb_attn_args {
 int ovb_attn_fwd(const ovb_attn_args* args, void* stream);
 /* Upper bound of the scratch ovb_attn_fwd can use for these shapes (0: the launch has no partial wave). */
 int64_t ovb_attn_workspace_size(const ovb_attn_args* args);
+/* Host-only: the work decomposition ovb_attn_fwd would use for these args (shapes, k_lens, workspace,
+ * no_split): n_whole items run as one CTA each, the n_tail items of the last partial wave are cut
+ * `parts` ways along the keys (n_tail = 0, parts = 1: no split).  Launches nothing. */
+int ovb_attn_plan(const ovb_attn_args* args, int32_t* n_whole, int32_t* n_tail, int32_t* parts);
 
 /* ---- peer transport: cross-GPU signal / wait ---------------------------------------------------
  * Every rank owns a pad of >= world uint32 flags in memory that all ranks have mapped

@@ -114,6 +114,8 @@ _SIGNATURES = {
     "ovb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "ovb_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
     "ovb_attn_workspace_size": (C.c_int64, [C.POINTER(AttnArgs)]),
+    "ovb_attn_plan": (C.c_int, [C.POINTER(AttnArgs), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                C.POINTER(C.c_int32)]),
     "ovb_peer_signal_wait": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "ovb_enable_peer_access": (C.c_int, [C.c_int32]),

@@ -601,6 +601,22 @@ static AttnSplit plan_split(const ovb_attn_args* a, int min_k_len) {
 
 }  // namespace ovb
 
+extern "C" int ovb_attn_plan(const ovb_attn_args* a, int32_t* n_whole, int32_t* n_tail, int32_t* parts) {
+  using namespace ovb;
+  OVB_CHECK_ARG(a != nullptr && n_whole && n_tail && parts, "ovb_attn_plan: null pointer");
+  OVB_CHECK_ARG(a->B > 0 && a->B <= 8 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "ovb_attn_plan: bad shape");
+  int min_kl = a->Lk;
+  for (int b = 0; b < a->B; ++b) {
+    const int kl = a->k_lens != nullptr ? a->k_lens[b] : a->Lk;
+    if (kl < min_kl) min_kl = kl;
+  }
+  const AttnSplit sp = plan_split(a, min_kl);
+  *n_whole = sp.n_whole;
+  *n_tail = sp.n_tail;
+  *parts = sp.parts;
+  return OVB_OK;
+}
+
 extern "C" int64_t ovb_attn_workspace_size(const ovb_attn_args* a) {
   if (a == nullptr || a->Lq <= 0 || a->H <= 0 || a->B <= 0) return 0;
   const long long T = static_cast<long long>((a->Lq + 255) / 256) * a->H * a->B;

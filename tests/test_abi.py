@@ -49,3 +49,47 @@ def test_no_fallback_without_cuda():
     lib = _lib.load()
     assert lib.ovb_check_device() != 0  # no sm_100 device here -> loud failure, not a silent path
     assert lib.ovb_last_error()
+
+
+def _plan(B, H, Lq, Lk, ws_bytes, k_lens=None, no_split=0):
+    import ctypes as C
+    from omni_video_b200 import _lib
+    lib = _lib.load()
+    a = _lib.AttnArgs()
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    if k_lens is not None:
+        arr = (C.c_int32 * B)(*k_lens)
+        a.k_lens = C.cast(arr, C.POINTER(C.c_int32))
+    a.no_split = no_split
+    if ws_bytes:
+        a.workspace, a.workspace_bytes = 0x1000, ws_bytes      # never dereferenced by the planner
+    need = int(lib.ovb_attn_workspace_size(C.byref(a)))
+    nw, nt, parts = C.c_int32(), C.c_int32(), C.c_int32()
+    assert lib.ovb_attn_plan(C.byref(a), C.byref(nw), C.byref(nt), C.byref(parts)) == 0
+    return nw.value, nt.value, parts.value, need
+
+
+def test_attention_work_decomposition_host_logic():
+    """ovb_attn_plan is host-only (no launch): the last partial wave of (q block, head, sample) items is
+    key-split only when a workspace is there, the slices stay long, and the saving is worth it."""
+    big = 1 << 30
+    # per-rank shape of cfg2 x ulysses4 on 8 GPUs: 128 q blocks x 3 heads = 384 items = 2 waves of 148 + 88
+    nw, nt, parts, need = _plan(1, 3, 32760, 32760, big)
+    assert (nw, nt) == (296, 88) and parts >= 3 and nw + nt == 384
+    assert need >= nt * parts * 256 * (128 * 4 + 8)
+    # rounds with the split are fewer than the 3 of the unsplit launch
+    assert 2 + -(-nt * parts // 148) / parts < 3
+    # no workspace / too small / disabled -> one CTA per item
+    assert _plan(1, 3, 32760, 32760, 0)[1:3] == (0, 1)
+    assert _plan(1, 3, 32760, 32760, 1024)[1:3] == (0, 1)
+    assert _plan(1, 3, 32760, 32760, big, no_split=1)[1:3] == (0, 1)
+    # single GPU, CFG-batched: 3072 items = 20.76 waves, the tail is not worth a split
+    assert _plan(2, 12, 32760, 32760, big)[1:3] == (0, 1)
+    # a full last wave needs nothing, and reports a zero workspace
+    assert _plan(1, 1, 148 * 256, 8192, big) == (148, 0, 1, 0)
+    # cross-attention: 512 keys are too few to cut
+    assert _plan(1, 3, 32760, 512, big)[1:3] == (0, 1)
+    # the shortest sample of a ragged batch decides how far the keys can be cut
+    long_ = _plan(2, 1, 1280, 8192, big, k_lens=[8192, 8192])
+    short = _plan(2, 1, 1280, 8192, big, k_lens=[8192, 1100])
+    assert long_[2] > short[2] >= 1
