@@ -601,6 +601,19 @@ class WanModel(nn.Module):
                                                   sp_group=getattr(self, "sp_group", None))
         return self._engine.forward(x, t, context, seq_len, y)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, **kwargs):
+        """diffusers `ModelMixin.from_pretrained` for a local directory (config.json + safetensors / .bin),
+        the call the reference makes at unified_model.py:43."""
+        from ..utils.checkpoint import wan_from_pretrained
+        return wan_from_pretrained(pretrained_model_name_or_path, subfolder=subfolder, torch_dtype=torch_dtype,
+                                   **kwargs)
+
+    def save_pretrained(self, save_directory, max_shard_size=5 << 30, safe_serialization=True):
+        from ..utils.checkpoint import save_wan_pretrained
+        save_wan_pretrained(self, save_directory, max_shard_bytes=max_shard_size,
+                            safe_serialization=safe_serialization)
+
     def unpatchify(self, x, grid_sizes):
         """reference model.py:526-549; x: list/batch of [L, out_dim*4] fp32."""
         grids = grid_sizes.tolist() if torch.is_tensor(grid_sizes) else grid_sizes

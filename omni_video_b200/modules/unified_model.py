@@ -84,10 +84,7 @@ class UnifiedWanWithMixedConditionModel(nn.Module):
     ):
         super().__init__()
         if isinstance(wan_model_or_ckpt_dir, str):
-            raise NotImplementedError(
-                "loading a WanModel checkpoint directory is the checkpoint-loader row (SURVEY.md §8(f) #3, "
-                "not built); construct from `wan_config` or pass a WanModel and use load_state_dict — "
-                "parameter names are the reference's")
+            self.wan_model = WanModel.from_pretrained(wan_model_or_ckpt_dir, subfolder=wan_subfolder)
         elif isinstance(wan_model_or_ckpt_dir, WanModel):
             self.wan_model = wan_model_or_ckpt_dir
         elif wan_config is not None:
@@ -272,7 +269,7 @@ class UnifiedWanWithMixedConditionModel(nn.Module):
     # ------------------------------------------------------------------ persistence (reference :280-285)
     def save_pretrained(self, save_dir: str):
         os.makedirs(save_dir, exist_ok=True)
-        torch.save(self.wan_model.state_dict(), os.path.join(save_dir, "wan_model.pt"))
+        self.wan_model.save_pretrained(os.path.join(save_dir, "wan_model"))
         if self.visual_context_adapter is not None:
             torch.save(self.visual_context_adapter.state_dict(),
                        os.path.join(save_dir, "visual_context_adapter_pytorch_model.bin"))
