@@ -1,5 +1,10 @@
 // Microbenchmark: cycles per element of the attention softmax inner loop variants, one warp per
 // scheduler (4 warps per CTA, one CTA per SM), data in registers.
+// NOTE (kept as a record of a measurement trap): an earlier version carried only s[t] of every group of
+// four through the `it` loop; s[t+1..t+3] were loop-invariant, nvcc hoisted their FFMA/MUFU out of the
+// loop, and the "654 cycles per 128-element pass" it reported was a quarter of the real MUFU work.  All
+// four elements are loop-carried now.  The numbers DESIGN.md quotes come from tmem_rate.cu / xu_rate.cu,
+// which reload the scores from TMEM every iteration.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o softmax_rate softmax_rate.cu -I ../../omni_video_b200/csrc
 #include <cstdio>
 #include <cstdlib>
@@ -48,7 +53,11 @@ __global__ void __launch_bounds__(128, 1) k(const float* in, uint32_t* out, int 
       if (V == 0 || V == 4 || V == 5 || V == 7) { sink ^= pack_bf16x2(e0, e1); sink ^= pack_bf16x2(e2, e3); }
       else if (V == 3 || V == 6) { sink ^= pack_bf16x2_alu(e0, e1); sink ^= pack_bf16x2_alu(e2, e3); }
       else { sink ^= __float_as_uint(e0) ^ __float_as_uint(e1) ^ __float_as_uint(e2) ^ __float_as_uint(e3); }
-      s[t] += 1e-3f * __uint_as_float(sink & 0x3f800000u);   // loop-carried so iterations are not hoisted
+      // all four loop-carried, so that no part of an iteration can be hoisted
+      s[t] += 1e-3f * __uint_as_float(sink & 0x3f800000u);
+      s[t + 1] += 1e-3f * __uint_as_float(sink & 0x3f000000u);
+      s[t + 2] += 1e-3f * __uint_as_float(sink & 0x3e800000u);
+      s[t + 3] += 1e-3f * __uint_as_float(sink & 0x3e000000u);
     }
   }
   const long long t1 = clock64();
@@ -86,6 +95,9 @@ __global__ void __launch_bounds__(384, 1) kenv(const float* in, uint32_t* out, i
           acc_b = fadd2(acc_b, pack_f32x2(e2, e3));
           sink ^= pack_bf16x2(e0, e1); sink ^= pack_bf16x2(e2, e3);
           s[t] += 1e-3f * __uint_as_float(sink & 0x3f800000u);
+          s[t + 1] += 1e-3f * __uint_as_float(sink & 0x3f000000u);
+          s[t + 2] += 1e-3f * __uint_as_float(sink & 0x3e800000u);
+          s[t + 3] += 1e-3f * __uint_as_float(sink & 0x3e000000u);
         }
       }
       const long long t1 = clock64();

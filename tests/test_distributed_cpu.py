@@ -81,6 +81,10 @@ def _worker(rank, world, port, results):
         err = (out - ref[:, sl]).abs().max().item()
         assert err < 1e-5, err
 
+        # ---- gloo has no peer memory: the engine must be told to use the collective transport
+        from omni_video_b200.distributed import peer
+        assert peer.get_transport(g, torch.device("cpu"), 8, 256) is None
+
         # ---- fail-fast head divisibility (reference ulysses.py:33-38)
         bad = torch.randn(1, s, 3, D)
         try:
