@@ -14,8 +14,14 @@
 // so the owner of the row can rescale O in TMEM itself), exponentiates with ex2.approx in the
 // log2 domain, and writes bf16 P over the first 64 columns of its own S region (tcgen05.st).
 // Keys >= k_len are masked to -inf; K/V rows past the tensor end are zero-filled by TMA.
+// P is published in two parts (keys [0,96), then the rest) so that PV starts before the row is done;
+// the launch is a 1-D grid of (q block, head, sample) items whose last partial wave is cut along the
+// keys (AttnParams, plan_split, attn_combine_kernel); in the scatter form the epilogue stores every
+// row into the buffer of the sequence-parallel rank that owns it (out_row_ptr).
 //
 // FLOPs per CTA-step (one KV tile, both Q tiles): 4 * 128*128*128 MACs; bytes from L2: 64 KB.
+// Co-limited by MUFU.EX2 (8 cycles per warp instruction: 2048 XU cycles per step against 2848
+// tensor-pipe cycles) through the per-tile chain QK -> softmax -> PV -> QK; DESIGN.md §3.1.
 #include <type_traits>
 
 #include "host_util.h"

@@ -93,3 +93,44 @@ def test_attention_work_decomposition_host_logic():
     long_ = _plan(2, 1, 1280, 8192, big, k_lens=[8192, 8192])
     short = _plan(2, 1, 1280, 8192, big, k_lens=[8192, 1100])
     assert long_[2] > short[2] >= 1
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    """Bad shapes / alignments / counts come back as negative codes with a message (never an exception,
+    never a launch): the checks run before the first CUDA call, so this holds on a box without a GPU."""
+    import ctypes as C
+    from omni_video_b200 import _lib
+    lib = _lib.load()
+
+    def err():
+        return lib.ovb_last_error().decode()
+
+    g = _lib.GemmArgs()
+    g.A = g.W = g.out = 0x1000
+    g.M, g.N, g.K, g.lda, g.ldw, g.ldo = 128, 100, 64, 64, 64, 100      # N not a multiple of 8
+    assert lib.ovb_gemm_bf16(C.byref(g), None) < 0 and "multiples of 8" in err()
+
+    a = _lib.AttnArgs()
+    a.q = a.k = a.v = a.out = 0x1000
+    a.B, a.H, a.Lq, a.Lk = 9, 1, 128, 128                              # B > 8
+    assert lib.ovb_attn_fwd(C.byref(a), None) < 0 and "B <= 8" in err()
+    a.B = 1
+    a.q_row_stride = a.k_row_stride = a.v_row_stride = a.o_row_stride = 130   # not a multiple of 8
+    assert lib.ovb_attn_fwd(C.byref(a), None) < 0 and "strides" in err()
+
+    r = _lib.RmsRopeArgs()
+    r.x = r.weight = 0x1000
+    r.rows, r.d, r.ldx = 4, 100, 104                                   # d not a multiple of 8
+    assert lib.ovb_rmsnorm_rope(C.byref(r), None) < 0 and "multiple of 8" in err()
+    r.d, r.ldx, r.copy_only = 128, 128, 1                              # copy_only without destinations
+    assert lib.ovb_rmsnorm_rope(C.byref(r), None) < 0 and "copy_only" in err()
+
+    ln = _lib.LnArgs()
+    ln.x = ln.out = ln.a = ln.b = 0x1000
+    ln.rows, ln.d, ln.ldx, ln.ldo = 4, 8200, 8200, 8200                # d > 8192
+    assert lib.ovb_layernorm(C.byref(ln), None) < 0
+
+    assert lib.ovb_patchify3d(0x1000, 0, 0x1000, 256, 16, 1, 2, 2, 1, 4, 4, None) < 0 and "smaller than patch" in err()
+    pads = (C.c_void_p * 9)(*([0x1000] * 9))
+    assert lib.ovb_peer_signal_wait(pads, 0, 9, 1, None, None, None) < 0 and "rank/world" in err()
+    assert lib.ovb_attn_plan(None, None, None, None) < 0
