@@ -64,69 +64,51 @@ def _ident(t):
     return t
 
 
+# WanModel constructor defaults the reference applies when a key is missing from `wan_config`
+# (unified_model.py:50-61); the remaining keys are forwarded only when present (:63-67).
+_WAN_CONFIG_DEFAULTS = dict(patch_size=(1, 2, 2), dim=2048, ffn_dim=8192, freq_dim=256, num_heads=16,
+                            num_layers=32, window_size=(-1, -1), qk_norm=True, cross_attn_norm=True, eps=1e-6)
+_WAN_CONFIG_OPTIONAL = ("model_type", "text_len", "in_dim", "text_dim", "out_dim")
+
+
+def _wan_from_config(wan_config: Dict, skip_init: bool) -> WanModel:
+    kw = {k: wan_config.get(k, dflt) for k, dflt in _WAN_CONFIG_DEFAULTS.items()}
+    kw.update({k: wan_config[k] for k in _WAN_CONFIG_OPTIONAL if k in wan_config})
+    logging.info("WanModel from config, random weights (skip_init=%s)", skip_init)
+    return WanModel(**kw, skip_init=skip_init)
+
+
 class UnifiedWanWithMixedConditionModel(nn.Module):
-    def __init__(
-        self,
-        wan_model_or_ckpt_dir: Union[WanModel, str, None] = None,
-        wan_subfolder: Optional[str] = None,
-        vlm_in_dim: int = 4096,
-        precision_dtype: torch.dtype = torch.float32,
-        device_id: int = 0,
-        rank: int = 0,
-        dit_fsdp: bool = False,
-        use_usp: bool = False,
-        use_visual_context_adapter: bool = False,
-        visual_context_adapter_patch_size: tuple = None,
-        max_context_len: int = None,
-        eps: float = 1e-6,
-        wan_config: Optional[Dict] = None,
-        skip_init: bool = False,
-    ):
+    # the signature is the reference's (unified_model.py:22-38): pipelines construct it by keyword
+    def __init__(self, wan_model_or_ckpt_dir: Union[WanModel, str, None] = None, wan_subfolder: Optional[str] = None,
+                 vlm_in_dim: int = 4096, precision_dtype: torch.dtype = torch.float32, device_id: int = 0,
+                 rank: int = 0, dit_fsdp: bool = False, use_usp: bool = False,
+                 use_visual_context_adapter: bool = False, visual_context_adapter_patch_size: tuple = None,
+                 max_context_len: int = None, eps: float = 1e-6, wan_config: Optional[Dict] = None,
+                 skip_init: bool = False):
         super().__init__()
-        if isinstance(wan_model_or_ckpt_dir, str):
-            self.wan_model = WanModel.from_pretrained(wan_model_or_ckpt_dir, subfolder=wan_subfolder)
-        elif isinstance(wan_model_or_ckpt_dir, WanModel):
-            self.wan_model = wan_model_or_ckpt_dir
+        src = wan_model_or_ckpt_dir
+        if isinstance(src, WanModel):
+            wan = src
+        elif isinstance(src, str):
+            wan = WanModel.from_pretrained(src, subfolder=wan_subfolder)
         elif wan_config is not None:
-            logging.info("Initializing WanModel with random weights from config (skip_init=%s)", skip_init)
-            # reference unified_model.py:48-69
-            model_params = {
-                'patch_size': wan_config.get('patch_size', (1, 2, 2)),
-                'dim': wan_config.get('dim', 2048),
-                'ffn_dim': wan_config.get('ffn_dim', 8192),
-                'freq_dim': wan_config.get('freq_dim', 256),
-                'num_heads': wan_config.get('num_heads', 16),
-                'num_layers': wan_config.get('num_layers', 32),
-                'window_size': wan_config.get('window_size', (-1, -1)),
-                'qk_norm': wan_config.get('qk_norm', True),
-                'cross_attn_norm': wan_config.get('cross_attn_norm', True),
-                'eps': wan_config.get('eps', 1e-6),
-            }
-            for k in ('model_type', 'text_len', 'in_dim', 'text_dim', 'out_dim'):
-                if k in wan_config:
-                    model_params[k] = wan_config[k]
-            self.wan_model = WanModel(**model_params, skip_init=skip_init)
+            wan = _wan_from_config(wan_config, skip_init)
         else:
             raise ValueError("Either wan_model_or_ckpt_dir or wan_config must be provided")
+        self.wan_model = wan
+        if max_context_len is not None:            # the DiT pads/attends over this many context rows
+            wan.text_len = max_context_len
+        self.max_context_len = wan.text_len
 
-        if max_context_len is not None:
-            self.wan_model.text_len = max_context_len
-        self.max_context_len = self.wan_model.text_len
-
+        # VLM tokens -> text space; parameters only, the arithmetic is in `_vlm`
         self.vlm_norm = WanRMSNorm(vlm_in_dim, eps=eps)
-        self.vlm_proj = nn.Linear(vlm_in_dim, self.wan_model.text_dim)
-
+        self.vlm_proj = nn.Linear(vlm_in_dim, wan.text_dim)
+        self.visual_context_adapter = None
         if use_visual_context_adapter:
-            self.visual_context_adapter = VisualContextAdapter(
-                patch_size=(self.wan_model.patch_size if visual_context_adapter_patch_size is None
-                            else visual_context_adapter_patch_size),
-                in_channels=self.wan_model.in_dim,
-                hidden_dim=self.wan_model.dim,
-                out_dim=self.wan_model.text_dim,
-                eps=eps,
-            )
-        else:
-            self.visual_context_adapter = None
+            patch = visual_context_adapter_patch_size or wan.patch_size
+            self.visual_context_adapter = VisualContextAdapter(patch_size=patch, in_channels=wan.in_dim,
+                                                               hidden_dim=wan.dim, out_dim=wan.text_dim, eps=eps)
         self._ctx_cache: Dict = {}
         self.context_cache_hits = 0
         self.context_cache_misses = 0
@@ -145,18 +127,27 @@ class UnifiedWanWithMixedConditionModel(nn.Module):
     @torch.no_grad()
     def _vlm(self, tokens: torch.Tensor) -> torch.Tensor:
         """vlm_proj(vlm_norm(tokens)) (reference unified_model.py:195-206): bf16 [.., text_dim]."""
-        shp = tokens.shape
-        h = tokens.reshape(-1, shp[-1]).to(bf16).contiguous().clone()
+        lead, width = tokens.shape[:-1], tokens.shape[-1]
+        h = tokens.reshape(-1, width).to(bf16).contiguous().clone()        # normalised in place below
         ops.rmsnorm_rope_(h, self.vlm_norm.weight.data.to(bf16).contiguous(), self.vlm_norm.eps)
         out = ops.gemm(h, self.vlm_proj.weight.data.to(bf16).contiguous(),
                        self.vlm_proj.bias.data.to(bf16).contiguous())
-        return out.view(*shp[:-1], out.shape[-1])
+        return out.view(*lead, out.shape[-1])
 
     def _params_key(self):
         ps = [self.vlm_norm.weight, self.vlm_proj.weight, self.vlm_proj.bias]
         if self.visual_context_adapter is not None:
             ps += list(self.visual_context_adapter.parameters())
         return tuple((p.data_ptr(), p._version) for p in ps)
+
+    def _per_sample(self, fn, batched, batch_size):
+        """Apply `fn` to a per-sample list (None entries stay None) or to a batched tensor as a whole —
+        the two input conventions of reference unified_model.py:195-217."""
+        if batched is None:
+            return None
+        if isinstance(batched, list):
+            return [None if batched[i] is None else fn(batched[i]) for i in range(batch_size)]
+        return fn(batched)
 
     @torch.no_grad()
     def mixed_context(self, batch_size, context=None, ar_vision_input=None, visual_emb=None,
@@ -172,109 +163,91 @@ class UnifiedWanWithMixedConditionModel(nn.Module):
             return hit
         self.context_cache_misses += 1
 
-        vlm_output = None if ar_vision_input is None else [None] * batch_size
-        if ar_vision_input is not None:
-            if isinstance(ar_vision_input, list):
-                for idx in range(batch_size):
-                    if ar_vision_input[idx] is not None:
-                        vlm_output[idx] = self._vlm(ar_vision_input[idx])
+        vlm = self._per_sample(self._vlm, ar_vision_input, batch_size)
+        visual = None
+        if visual_emb is not None:
+            adapter = self.visual_context_adapter
+            if adapter is None:
+                visual = [None] * batch_size       # the reference keeps the slots and fills none (:209-217)
+            elif isinstance(visual_emb, list):
+                visual = self._per_sample(lambda v: adapter(v).squeeze(0), visual_emb, batch_size)
             else:
-                vlm_output = self._vlm(ar_vision_input)
+                visual = adapter(visual_emb)
 
-        processed_visual = None if visual_emb is None else [None] * batch_size
-        if visual_emb is not None and self.visual_context_adapter is not None:
-            if isinstance(visual_emb, list):
-                for idx in range(batch_size):
-                    if visual_emb[idx] is not None:
-                        processed_visual[idx] = self.visual_context_adapter(visual_emb[idx]).squeeze(0)
-            else:
-                processed_visual = self.visual_context_adapter(visual_emb)
-
+        tok = (lambda name: _item(special_token_dict.get(name), None, batch_size)) if special_token_dict else None
         mixed = []
         for idx in range(batch_size):
-            vlm_item = _item(vlm_output, idx, batch_size)
-            context_item = _item(context, idx, batch_size)
-            visual_item = _item(processed_visual, idx, batch_size)
-            components = []
-            if special_token_dict is not None:
-                img_st = _item(special_token_dict.get('<img_st>'), None, batch_size)
-                img_ed = _item(special_token_dict.get('<img_ed>'), None, batch_size)
-                prp_st = _item(special_token_dict.get('<prp_st>'), None, batch_size)
-                prp_ed = _item(special_token_dict.get('<prp_ed>'), None, batch_size)
-                if vlm_item is not None:
-                    components.append(vlm_item)
-                if context_item is not None:
-                    components.extend([prp_st, context_item, prp_ed])
-                if visual_item is not None:
-                    components.extend([img_st, visual_item, img_ed])
-            else:
-                components = [c for c in (vlm_item, context_item, visual_item) if c is not None]
-            components = [c for c in components if c is not None]
-            if components:
-                dev = device if device is not None else components[0].device
-                new_context = torch.cat([c.to(device=dev, dtype=bf16) for c in components], dim=0)
-                if self.max_context_len is not None and new_context.shape[0] > self.max_context_len:
-                    new_context = new_context[:self.max_context_len]
-                mixed.append(new_context)
-            else:
+            parts = {"vlm": _item(vlm, idx, batch_size), "text": _item(context, idx, batch_size),
+                     "visual": _item(visual, idx, batch_size)}
+            seq = []
+            if tok is None:                         # no markers: VLM | text | visual
+                seq = [parts[k] for k in ("vlm", "text", "visual")]
+            else:                                   # VLM | <prp_st> text <prp_ed> | <img_st> visual <img_ed>
+                seq.append(parts["vlm"])
+                if parts["text"] is not None:
+                    seq += [tok("<prp_st>"), parts["text"], tok("<prp_ed>")]
+                if parts["visual"] is not None:
+                    seq += [tok("<img_st>"), parts["visual"], tok("<img_ed>")]
+            seq = [c for c in seq if c is not None]
+            if not seq:                             # nothing to attend to: one zero row (:273-274)
                 mixed.append(torch.zeros(1, self.wan_model.text_dim, device=device, dtype=bf16))
+                continue
+            dev = device if device is not None else seq[0].device
+            rows = torch.cat([c.to(device=dev, dtype=bf16) for c in seq], dim=0)
+            mixed.append(rows[:self.max_context_len] if self.max_context_len is not None else rows)
         if len(self._ctx_cache) >= 8:          # two entries per prompt (cond / uncond) are live at a time
             self._ctx_cache.pop(next(iter(self._ctx_cache)))
         self._ctx_cache[key] = mixed
         return mixed
 
-    def forward(
-        self,
-        x: List[torch.Tensor],
-        t: torch.Tensor,
-        context: List[torch.Tensor] = None,
-        aligned_emb: Optional[torch.Tensor] = None,
-        ar_vision_input: Optional[List[torch.Tensor]] = None,
-        visual_emb: Optional[torch.Tensor] = None,
-        seq_len: Optional[int] = None,
-        special_token_dict: Optional[Dict[str, torch.Tensor]] = None,
-        classifier_free_ratio: Optional[float] = None,
-        unconditioned_context: Optional[Dict[str, torch.Tensor]] = None,
-        condition_mode: str = "auto",
-    ):
-        if condition_mode == "auto":
-            condition_mode = "full"
-        batch_size = x.size(0) if isinstance(x, torch.Tensor) else len(x)
-        if condition_mode != "full":
+    @staticmethod
+    def _condition_dropout(batch_size, context, ar_vision_input, classifier_free_ratio, unconditioned_context):
+        """Training-time CFG (reference unified_model.py:157-190).  Two `random.random()` draws per sample
+        are consumed on EVERY call, used or not, so Python's RNG stream matches the reference's; the second
+        set belongs to a branch whose threshold upstream is 0.00 (never taken)."""
+        drop = [random.random() for _ in range(batch_size)]
+        _unused = [random.random() for _ in range(batch_size)]
+        if not classifier_free_ratio or classifier_free_ratio <= 0:
+            return
+        for idx, r in enumerate(drop):
+            if r >= classifier_free_ratio:
+                continue
+            if unconditioned_context is None:
+                raise ValueError("unconditioned_context must be provided when classifier_free_ratio > 0")
+            if not isinstance(unconditioned_context, dict):
+                continue
+            if ar_vision_input is not None and ar_vision_input[idx] is not None:
+                v = ar_vision_input[idx]            # null VLM condition: two near-zero tokens
+                ar_vision_input[idx] = torch.zeros(2, v.size(1), device=v.device, dtype=v.dtype) + 1e-6
+            if context is not None and context[idx] is not None and "uncond_context" in unconditioned_context:
+                context[idx] = unconditioned_context["uncond_context"]
+
+    def forward(self, x: List[torch.Tensor], t: torch.Tensor, context: List[torch.Tensor] = None,
+                aligned_emb: Optional[torch.Tensor] = None, ar_vision_input: Optional[List[torch.Tensor]] = None,
+                visual_emb: Optional[torch.Tensor] = None, seq_len: Optional[int] = None,
+                special_token_dict: Optional[Dict[str, torch.Tensor]] = None,
+                classifier_free_ratio: Optional[float] = None,
+                unconditioned_context: Optional[Dict[str, torch.Tensor]] = None, condition_mode: str = "auto"):
+        """Same keywords as reference unified_model.py:138-152; returns what `WanModel.forward` returns."""
+        if condition_mode not in ("auto", "full"):
             # the reference's forward has no other branch: it falls off the end and returns None, which
             # its caller then indexes.  Fail here with the reason instead.
             raise ValueError(f"condition_mode={condition_mode!r}: only 'full' / 'auto' are implemented "
                              "(reference unified_model.py:152-158 has no other branch either)")
-
-        # 1. condition dropout (training-time CFG).  Both draws happen for every sample on every
-        #    call, whether used or not (reference unified_model.py:160-162).
-        cfg_rands = [random.random() for _ in range(batch_size)]
-        _ar_only_rands = [random.random() for _ in range(batch_size)]  # threshold is 0.00 upstream: never taken
-        for idx in range(batch_size):
-            r = cfg_rands[idx]
-            if classifier_free_ratio is not None and classifier_free_ratio > 0 and r < classifier_free_ratio:
-                if unconditioned_context is None:
-                    raise ValueError("unconditioned_context must be provided when classifier_free_ratio > 0")
-                if isinstance(unconditioned_context, dict):
-                    if ar_vision_input is not None and ar_vision_input[idx] is not None:
-                        v = ar_vision_input[idx]
-                        ar_vision_input[idx] = torch.zeros(2, v.size(1), device=v.device, dtype=v.dtype) + 1e-6
-                    if context is not None and context[idx] is not None and 'uncond_context' in unconditioned_context:
-                        context[idx] = unconditioned_context['uncond_context']
-
-        dev = x[0].device
-        mixed = self.mixed_context(batch_size, context, ar_vision_input, visual_emb, special_token_dict, dev)
+        batch_size = x.size(0) if isinstance(x, torch.Tensor) else len(x)
+        self._condition_dropout(batch_size, context, ar_vision_input, classifier_free_ratio, unconditioned_context)
+        mixed = self.mixed_context(batch_size, context, ar_vision_input, visual_emb, special_token_dict, x[0].device)
         return self.wan_model(x, t=t, context=mixed, seq_len=seq_len)
 
     # ------------------------------------------------------------------ persistence (reference :280-285)
     def save_pretrained(self, save_dir: str):
         os.makedirs(save_dir, exist_ok=True)
         self.wan_model.save_pretrained(os.path.join(save_dir, "wan_model"))
+        parts = {"vlm_norm": self.vlm_norm, "vlm_proj": self.vlm_proj}
         if self.visual_context_adapter is not None:
-            torch.save(self.visual_context_adapter.state_dict(),
-                       os.path.join(save_dir, "visual_context_adapter_pytorch_model.bin"))
-        torch.save(self.vlm_norm.state_dict(), os.path.join(save_dir, "vlm_norm_pytorch_model.bin"))
-        torch.save(self.vlm_proj.state_dict(), os.path.join(save_dir, "vlm_proj_pytorch_model.bin"))
+            parts["visual_context_adapter"] = self.visual_context_adapter
+        for name, mod in parts.items():
+            torch.save(mod.state_dict(), os.path.join(save_dir, f"{name}_pytorch_model.bin"))
 
     def enable_eval(self):
         self.eval()
