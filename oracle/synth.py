@@ -220,3 +220,45 @@ def unified_inputs(cfg: dict, vlm_in_dim: int, n_vlm, n_text, visual_grid, seed:
     if all(a is None for a in ar):
         ar = None
     return ar, ctx, vis, st
+
+
+# ------------------------------------------------------------------------------- umT5 encoder
+TINY_T5 = dict(vocab=97, dim=128, dim_attn=128, dim_ffn=256, num_heads=2, num_layers=2, num_buckets=32,
+               shared_pos=False)          # head_dim 64 like umT5-XXL (4096 / 64 heads)
+
+
+def t5_state_dict(cfg: dict, seed: int = 1818) -> Dict[str, torch.Tensor]:
+    """fp32 state dict of the reference's T5Encoder (t5.py:266-297); scales follow its init_weights (:26-44)
+    except that norm weights are perturbed around 1 so that they matter."""
+    rng = np.random.default_rng(seed + 7)
+    d, da, df, nh, nb = cfg["dim"], cfg["dim_attn"], cfg["dim_ffn"], cfg["num_heads"], cfg["num_buckets"]
+    sd = {"token_embedding.weight": _normal(rng, (cfg["vocab"], d), 1.0)}
+    if cfg.get("shared_pos"):
+        sd["pos_embedding.embedding.weight"] = _normal(rng, (nb, nh), 0.5)
+    for i in range(cfg["num_layers"]):
+        p = f"blocks.{i}."
+        sd[p + "norm1.weight"] = 1.0 + _normal(rng, (d,), 0.05)
+        sd[p + "attn.q.weight"] = _normal(rng, (da, d), (d * (da // nh)) ** -0.5 * 4)
+        sd[p + "attn.k.weight"] = _normal(rng, (da, d), d ** -0.5)
+        sd[p + "attn.v.weight"] = _normal(rng, (da, d), d ** -0.5)
+        sd[p + "attn.o.weight"] = _normal(rng, (d, da), da ** -0.5)
+        sd[p + "norm2.weight"] = 1.0 + _normal(rng, (d,), 0.05)
+        sd[p + "ffn.gate.0.weight"] = _normal(rng, (df, d), d ** -0.5)
+        sd[p + "ffn.fc1.weight"] = _normal(rng, (df, d), d ** -0.5)
+        sd[p + "ffn.fc2.weight"] = _normal(rng, (d, df), df ** -0.5)
+        if not cfg.get("shared_pos"):
+            sd[p + "pos_embedding.embedding.weight"] = _normal(rng, (nb, nh), 0.5)
+    sd["norm.weight"] = 1.0 + _normal(rng, (d,), 0.05)
+    return sd
+
+
+def t5_inputs(cfg: dict, lengths, seq_len: int, seed: int = 7):
+    """ids [B, seq_len] (0-padded, as the tokenizer pads to text_len) and mask [B, seq_len]."""
+    rng = np.random.default_rng(seed + 3)
+    B = len(lengths)
+    ids = torch.zeros(B, seq_len, dtype=torch.int64)
+    mask = torch.zeros(B, seq_len, dtype=torch.int64)
+    for b, n in enumerate(lengths):
+        ids[b, :n] = torch.from_numpy(rng.integers(1, cfg["vocab"], size=n))
+        mask[b, :n] = 1
+    return ids, mask
