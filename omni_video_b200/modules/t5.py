@@ -1,0 +1,244 @@
+"""umT5 encoder on the B200 kernels (drop-in for the ENCODER half of reference omnivideo/modules/t5.py;
+SURVEY.md §8(f) #4).  STATUS: composed from kernels that are individually parity-green, host logic checked on
+CPU against the reference's goldens with the kernels emulated (tests/test_t5_cpu.py); NOT yet run on a GPU.
+
+The text encoder is 4.7 TFLOP per 512-token prompt and runs twice per sample — under 0.02 % of a 50-step
+sample — so nothing here is tuned; the point is that the reference's `T5EncoderModel(...)(texts, device)` keeps
+working without PyTorch arithmetic on the device.  Parameter names are the reference's (`token_embedding`,
+`blocks.{i}.{norm1,attn.{q,k,v,o},norm2,ffn.{gate.0,fc1,fc2},pos_embedding.embedding}`, `norm`), so
+`models_t5_umt5-xxl-enc-bf16.pth` loads unchanged.
+
+    reference (t5.py)                                            kernel
+    -----------------------------------------------------------  ------------------------------------------
+    T5LayerNorm :55-64 (RMS, cast to bf16 before the weight)     ovb_rmsnorm_rope (rope = 0)
+    q | k = x W^T (no bias) :96-98                               ovb_gemm_bf16 (fused [Wq; Wk])
+    V^T = Wv x^T                                                 ovb_gemm_bf16 (A = Wv, W = x: no transpose copy)
+    scores + position bias + key mask :101-110 (NO 1/sqrt(d))    ovb_gemm_bf16 RESID_F32 into a buffer preloaded
+                                                                 with the [L, keys] bias (-3e38 on padding keys)
+    softmax in fp32 :111                                         ovb_softmax_rows
+    P V, o-projection + residual :112-117, :169                  ovb_gemm_bf16, ovb_gemm_bf16 RESID_BF16
+    fc1(x) * GELU_tanh(gate(x)) :133-138                         ovb_gemm_bf16 GELU_BF16 -> fp32 gate table ->
+                                                                 ovb_gemm_bf16 GATE_RESID_F32 on a zero residual
+    fc2 + residual :170                                          ovb_gemm_bf16 RESID_BF16
+
+The relative-position bucket table (t5.py:241-263) is integer arithmetic on positions: computed once per
+sequence length on the host, like the reference does.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops, vae_ops
+from ..ops import EPI_BF16, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_RESID_BF16, EPI_RESID_F32
+
+__all__ = ["T5Encoder", "T5EncoderModel", "umt5_xxl"]
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+_NEG = -3.0e38          # additive mask for padding keys (the reference uses finfo.min, t5.py:108)
+
+
+class T5LayerNorm(nn.Module):
+    def __init__(self, dim, eps=1e-6):
+        super().__init__()
+        self.dim, self.eps = dim, eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class T5Attention(nn.Module):
+    def __init__(self, dim, dim_attn, num_heads, dropout=0.1):
+        assert dim_attn % num_heads == 0
+        super().__init__()
+        self.dim, self.dim_attn, self.num_heads, self.head_dim = dim, dim_attn, num_heads, dim_attn // num_heads
+        self.q = nn.Linear(dim, dim_attn, bias=False)
+        self.k = nn.Linear(dim, dim_attn, bias=False)
+        self.v = nn.Linear(dim, dim_attn, bias=False)
+        self.o = nn.Linear(dim_attn, dim, bias=False)
+
+
+class T5FeedForward(nn.Module):
+    def __init__(self, dim, dim_ffn, dropout=0.1):
+        super().__init__()
+        self.dim, self.dim_ffn = dim, dim_ffn
+        self.gate = nn.Sequential(nn.Linear(dim, dim_ffn, bias=False), nn.GELU(approximate="tanh"))
+        self.fc1 = nn.Linear(dim, dim_ffn, bias=False)
+        self.fc2 = nn.Linear(dim_ffn, dim, bias=False)
+
+
+class T5RelativeEmbedding(nn.Module):
+    def __init__(self, num_buckets, num_heads, bidirectional, max_dist=128):
+        super().__init__()
+        self.num_buckets, self.num_heads, self.bidirectional, self.max_dist = num_buckets, num_heads, bidirectional, max_dist
+        self.embedding = nn.Embedding(num_buckets, num_heads)
+
+    def buckets(self, lq: int, lk: int) -> torch.Tensor:
+        """[lq, lk] int64 bucket index of (key position - query position); reference :241-263."""
+        if not self.bidirectional:
+            raise NotImplementedError("only the encoder's bidirectional table is on the path")
+        rel = torch.arange(lk).unsqueeze(0) - torch.arange(lq).unsqueeze(1)
+        half = self.num_buckets // 2
+        out = (rel > 0).long() * half
+        rel = rel.abs()
+        exact = half // 2
+        far = exact + (torch.log(rel.float() / exact) / math.log(self.max_dist / exact) * (half - exact)).long()
+        far = torch.minimum(far, torch.full_like(far, half - 1))
+        return out + torch.where(rel < exact, rel, far)
+
+
+class T5SelfAttention(nn.Module):
+    def __init__(self, dim, dim_attn, dim_ffn, num_heads, num_buckets, shared_pos=True, dropout=0.1):
+        super().__init__()
+        self.shared_pos = shared_pos
+        self.norm1 = T5LayerNorm(dim)
+        self.attn = T5Attention(dim, dim_attn, num_heads, dropout)
+        self.norm2 = T5LayerNorm(dim)
+        self.ffn = T5FeedForward(dim, dim_ffn, dropout)
+        self.pos_embedding = None if shared_pos else T5RelativeEmbedding(num_buckets, num_heads, bidirectional=True)
+
+
+def _w(p: torch.Tensor) -> torch.Tensor:
+    return p.detach().to(bf16).contiguous()
+
+
+class T5Encoder(nn.Module):
+    """reference t5.py:266-311; `forward(ids [B, L], mask [B, L] | None) -> bf16 [B, L, dim]`."""
+
+    def __init__(self, vocab, dim, dim_attn, dim_ffn, num_heads, num_layers, num_buckets, shared_pos=True,
+                 dropout=0.1):
+        super().__init__()
+        self.dim, self.dim_attn, self.dim_ffn = dim, dim_attn, dim_ffn
+        self.num_heads, self.num_layers, self.num_buckets, self.shared_pos = num_heads, num_layers, num_buckets, shared_pos
+        self.token_embedding = vocab if isinstance(vocab, nn.Embedding) else nn.Embedding(vocab, dim)
+        self.pos_embedding = T5RelativeEmbedding(num_buckets, num_heads, bidirectional=True) if shared_pos else None
+        self.blocks = nn.ModuleList([T5SelfAttention(dim, dim_attn, dim_ffn, num_heads, num_buckets, shared_pos, dropout)
+                                     for _ in range(num_layers)])
+        self.norm = T5LayerNorm(dim)
+        self._packed = None
+        self._bucket_cache = {}
+
+    # packed bf16 weights (fused [Wq; Wk]): a derived cache, rebuilt when parameters move or change
+    def _weights(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or self._packed[0] != key:
+            layers = []
+            for blk in self.blocks:
+                a, f = blk.attn, blk.ffn
+                layers.append(dict(n1=_w(blk.norm1.weight), qk=_w(torch.cat([a.q.weight, a.k.weight], 0)), v=_w(a.v.weight),
+                                   o=_w(a.o.weight), n2=_w(blk.norm2.weight), gate=_w(f.gate[0].weight),
+                                   fc1=_w(f.fc1.weight), fc2=_w(f.fc2.weight)))
+            self._packed = (key, layers, _w(self.norm.weight))
+        return self._packed[1], self._packed[2]
+
+    def _bias(self, table: torch.Tensor, L: int, keys: int, n_valid: int) -> torch.Tensor:
+        """fp32 [heads, L, keys]: position bias of the first `keys` key positions, -3e38 on keys >= n_valid."""
+        dev = table.device
+        b = self._bucket_cache.get((L, str(dev)))
+        if b is None:
+            rel = (self.pos_embedding or self.blocks[0].pos_embedding).buckets(L, L)
+            b = self._bucket_cache[(L, str(dev))] = rel.to(dev)
+        bias = table.float()[b[:, :keys]].permute(2, 0, 1).contiguous()
+        if n_valid < keys:
+            bias[:, :, n_valid:] = _NEG
+        return bias
+
+    @torch.no_grad()
+    def _encode_one(self, ids: torch.Tensor, n_valid: int) -> torch.Tensor:
+        layers, norm_w = self._weights()
+        L, d, da, nh, hd, eps = ids.shape[0], self.dim, self.dim_attn, self.num_heads, self.dim_attn // self.num_heads, 1e-6
+        dev = ids.device
+        if L % 64 != 0:
+            raise NotImplementedError(f"sequence length {L} must be a multiple of 64 (the pipeline pads to text_len 512)")
+        keys = (n_valid + 63) // 64 * 64                    # key columns the score GEMMs cover; the rest is padding
+        x = self.token_embedding.weight.detach()[ids].to(bf16).contiguous()          # [L, d]
+        h = torch.empty_like(x)
+        qk = torch.empty((L, 2 * da), device=dev, dtype=bf16)
+        vt = torch.empty((da, keys), device=dev, dtype=bf16)
+        S = torch.empty((L, keys), device=dev, dtype=f32)
+        P = torch.empty((L, keys), device=dev, dtype=bf16)
+        att = torch.empty((L, da), device=dev, dtype=bf16)
+        zero = torch.zeros((L, self.dim_ffn), device=dev, dtype=f32)
+        shared = None if self.pos_embedding is None else self._bias(self.pos_embedding.embedding.weight.detach(), L, keys, n_valid)
+        for blk, W in zip(self.blocks, layers):
+            bias = shared if shared is not None else self._bias(blk.pos_embedding.embedding.weight.detach(), L, keys, n_valid)
+            # ---- self attention (no 1/sqrt(d) scaling in T5)
+            h.copy_(x)
+            ops.rmsnorm_rope_(h, W["n1"], eps)
+            ops.gemm(h, W["qk"], None, epilogue=EPI_BF16, out=qk)
+            ops.gemm(W["v"], h[:keys], None, epilogue=EPI_BF16, out=vt)                 # V^T [da, keys]
+            for i in range(nh):
+                cols = slice(i * hd, (i + 1) * hd)
+                S.copy_(bias[i])
+                ops.gemm(qk[:, cols], qk[:keys, da + i * hd:da + (i + 1) * hd], None, epilogue=EPI_RESID_F32,
+                         out=S, resid=S)                                                  # bias + q k^T
+                vae_ops.softmax_rows(S, 1.0, out=P)
+                ops.gemm(P, vt[cols], None, epilogue=EPI_BF16, out=att[:, cols])
+            ops.gemm(att, W["o"], None, epilogue=EPI_RESID_BF16, out=x, resid=x)
+            # ---- gated-GELU feed forward
+            h.copy_(x)
+            ops.rmsnorm_rope_(h, W["n2"], eps)
+            g = ops.cast_bf16_to_f32(ops.gemm(h, W["gate"], None, epilogue=EPI_GELU_BF16))
+            u = ops.gemm(h, W["fc1"], None, epilogue=EPI_GATE_RESID_F32, out=torch.zeros_like(zero), resid=zero, gate=g)
+            ops.gemm(ops.cast_f32_to_bf16(u), W["fc2"], None, epilogue=EPI_RESID_BF16, out=x, resid=x)
+        ops.rmsnorm_rope_(x, norm_w, eps)
+        return x
+
+    def forward(self, ids, mask=None):
+        if ids.device.type != "cuda":
+            raise RuntimeError("T5Encoder (B200 path) needs CUDA tensors; there is no CPU fallback")
+        outs = []
+        for b in range(ids.shape[0]):
+            n = ids.shape[1] if mask is None else int((mask[b] > 0).sum())
+            outs.append(self._encode_one(ids[b], max(n, 1)))
+        return torch.stack(outs)
+
+
+def umt5_xxl(encoder_only=True, return_tokenizer=False, dtype=bf16, device="cuda", **kwargs):
+    """reference t5.py:454-467 (encoder only: the decoder is not on the path)."""
+    if not encoder_only or return_tokenizer:
+        raise NotImplementedError("only `umt5_xxl(encoder_only=True, return_tokenizer=False)` is on the path")
+    cfg = dict(vocab=256384, dim=4096, dim_attn=4096, dim_ffn=10240, num_heads=64, num_layers=24, num_buckets=32,
+               shared_pos=False, dropout=0.1)
+    cfg.update(kwargs)
+    with torch.device(device):
+        model = T5Encoder(**cfg)
+    return model.to(dtype=dtype, device=device)
+
+
+class T5EncoderModel:
+    """reference t5.py:471-512: `T5EncoderModel(text_len, dtype, device, checkpoint_path, tokenizer_path)(texts, device)`
+    -> list of [n_tokens_i, 4096]."""
+
+    def __init__(self, text_len, dtype=bf16, device="cuda", checkpoint_path=None, tokenizer_path=None, shard_fn=None,
+                 tokenizer=None):
+        self.text_len, self.dtype, self.device = text_len, dtype, device
+        self.checkpoint_path, self.tokenizer_path = checkpoint_path, tokenizer_path
+        model = umt5_xxl(encoder_only=True, return_tokenizer=False, dtype=dtype, device=device).eval().requires_grad_(False)
+        if checkpoint_path is not None:
+            logging.info("loading %s", checkpoint_path)
+            model.load_state_dict(torch.load(checkpoint_path, map_location="cpu", weights_only=True))
+        self.model = model
+        if tokenizer is None:
+            try:        # the reference's HuggingfaceTokenizer(name, seq_len, clean='whitespace') needs `ftfy` + HF files
+                from transformers import AutoTokenizer
+                hf = AutoTokenizer.from_pretrained(tokenizer_path)
+
+                def tokenizer(texts, return_mask=True, add_special_tokens=True):
+                    texts = [" ".join(t.split()) for t in texts]                 # clean='whitespace'
+                    enc = hf(texts, return_tensors="pt", padding="max_length", truncation=True,
+                             max_length=text_len, add_special_tokens=add_special_tokens)
+                    return enc.input_ids, enc.attention_mask
+            except Exception as ex:  # noqa: BLE001
+                raise RuntimeError(f"cannot build the umT5 tokenizer from {tokenizer_path!r}: {ex}") from ex
+        self.tokenizer = tokenizer
+
+    def __call__(self, texts: List[str], device) -> List[torch.Tensor]:
+        ids, mask = self.tokenizer(texts, return_mask=True, add_special_tokens=True)
+        ids, mask = ids.to(device), mask.to(device)
+        seq_lens = mask.gt(0).sum(dim=1).long()
+        context = self.model(ids, mask)
+        return [u[:v] for u, v in zip(context, seq_lens)]
