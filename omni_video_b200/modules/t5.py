@@ -1,6 +1,7 @@
 """umT5 encoder on the B200 kernels (drop-in for the ENCODER half of reference omnivideo/modules/t5.py;
-SURVEY.md §8(f) #4).  STATUS: composed from kernels that are individually parity-green, host logic checked on
-CPU against the reference's goldens with the kernels emulated (tests/test_t5_cpu.py); NOT yet run on a GPU.
+SURVEY.md §8(f) #4).  Composed from the kernels of the DiT/VAE path; parity on the GPU against the oracle pinned
+to the reference's T5Encoder (tests/test_gpu_t5.py), host logic also on CPU with emulated kernels
+(tests/test_t5_cpu.py).
 
 The text encoder is 4.7 TFLOP per 512-token prompt and runs twice per sample — under 0.02 % of a 50-step
 sample — so nothing here is tuned; the point is that the reference's `T5EncoderModel(...)(texts, device)` keeps

@@ -1,8 +1,6 @@
-"""umT5 encoder (omni_video_b200/modules/t5.py) on the GPU against the fp32 oracle pinned to the reference's
-T5Encoder.  The module was written after the round's GPU budget was spent: its host logic is covered on CPU
-with emulated kernels (tests/test_t5_cpu.py) and every kernel it calls is parity-green on its own, but this
-file had not run on a B200 when it was committed — hence `xfail(strict=False)`: a pass is reported as XPASS,
-a failure does not turn the suite red.  It sorts last on purpose."""
+"""umT5 encoder (omni_video_b200/modules/t5.py) on the GPU against the fp32 oracle that is
+pinned to the reference's T5Encoder (tests/golden/t5_*.npz): ragged batch with padding keys, and a sequence
+whose distances exceed the 128-position bucket range."""
 import pytest
 import torch
 
@@ -10,8 +8,7 @@ from oracle import dit as O
 from oracle import synth
 from oracle import t5 as T
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120),
-              pytest.mark.xfail(strict=False, reason="first GPU run of modules/t5.py pending (written after the round's GPU budget)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
 
 @pytest.mark.parametrize("shared_pos,lengths,seq_len", [(False, [9, 64], 64), (False, [130], 256)])

@@ -2,7 +2,7 @@
 replaced by torch emulations WITH THEIR ROUNDING POINTS (bf16 GEMM results, fp32 score buffer, bf16 P ...), and
 the result is compared with the fp32 oracle that is pinned to the reference's T5Encoder.  This checks indexing,
 head slicing, the bias/mask matrix, the gated FFN plumbing and the residual flow; the kernels themselves are
-covered by tests/test_gpu_kernels.py / test_gpu_vae.py.  (First GPU run of this module: round 2.)"""
+covered by tests/test_gpu_kernels.py / test_gpu_vae.py, the module on the GPU by tests/test_gpu_t5.py."""
 import pytest
 import torch
 import torch.nn.functional as F
