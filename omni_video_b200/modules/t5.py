@@ -198,6 +198,20 @@ class T5Encoder(nn.Module):
         return torch.stack(outs)
 
 
+def clean_whitespace(text: str) -> str:
+    """`whitespace_clean(basic_clean(text))` of reference tokenizers.py:12-22: ftfy mojibake repair (when ftfy is
+    installed; it is a no-op on clean text), HTML entities unescaped twice, runs of whitespace collapsed."""
+    import html
+    import re
+    try:
+        import ftfy
+        text = ftfy.fix_text(text)
+    except ImportError:
+        pass
+    text = html.unescape(html.unescape(text)).strip()
+    return re.sub(r"\s+", " ", text).strip()
+
+
 def umt5_xxl(encoder_only=True, return_tokenizer=False, dtype=bf16, device="cuda", **kwargs):
     """reference t5.py:454-467 (encoder only: the decoder is not on the path)."""
     if not encoder_only or return_tokenizer:
@@ -224,12 +238,12 @@ class T5EncoderModel:
             model.load_state_dict(torch.load(checkpoint_path, map_location="cpu", weights_only=True))
         self.model = model
         if tokenizer is None:
-            try:        # the reference's HuggingfaceTokenizer(name, seq_len, clean='whitespace') needs `ftfy` + HF files
+            try:        # the reference's HuggingfaceTokenizer(name, seq_len, clean='whitespace'), tokenizers.py:37-82
                 from transformers import AutoTokenizer
                 hf = AutoTokenizer.from_pretrained(tokenizer_path)
 
                 def tokenizer(texts, return_mask=True, add_special_tokens=True):
-                    texts = [" ".join(t.split()) for t in texts]                 # clean='whitespace'
+                    texts = [clean_whitespace(t) for t in ([texts] if isinstance(texts, str) else texts)]
                     enc = hf(texts, return_tensors="pt", padding="max_length", truncation=True,
                              max_length=text_len, add_special_tokens=add_special_tokens)
                     return enc.input_ids, enc.attention_mask

@@ -85,3 +85,9 @@ def test_t5_state_dict_names_are_the_references():
         T5Encoder(**cfg)(torch.zeros(1, 64, dtype=torch.int64))          # no CPU fallback
     with pytest.raises(NotImplementedError):
         T5Encoder(**cfg)._encode_one(torch.zeros(24, dtype=torch.int64), 5)
+
+
+def test_prompt_cleaning_matches_reference_rules():
+    from omni_video_b200.modules.t5 import clean_whitespace
+    assert clean_whitespace("  a  cat\n\tsits &amp;amp; purrs  ") == "a cat sits & purrs"
+    assert clean_whitespace("plain") == "plain"
