@@ -345,6 +345,15 @@ int ovb_cl_to_planar(const void* src, int32_t Cs, const float* scale, const floa
 int ovb_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int32_t rows, int32_t cols,
                      float scale, void* stream);
 
+/* ---- output video path ---------------------------------------------------------------------------
+ * Decoded video -> uint8 frames, the tensor part of `cache_video` (reference omnivideo/utils/utils.py:177-185:
+ * clamp to value_range, normalise to [0, 1], x 255, truncate):
+ *   out[t * out_frame_stride + y * out_row_stride + x * C + c] = uint8((clamp(v, lo, hi) - lo) / max(hi - lo, 1e-5) * 255)
+ * x: planar fp32 [C, T, H, W] (what Wan2_1_VAE.decode returns), C <= 4; out: uint8, pitches in bytes, so one
+ * video can be written into a cell of a torchvision-style grid. */
+int ovb_video_to_uint8(const float* x, uint8_t* out, int32_t C, int32_t T, int32_t H, int32_t W,
+                       int64_t out_frame_stride, int64_t out_row_stride, float lo, float hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

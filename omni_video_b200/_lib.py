@@ -111,6 +111,8 @@ _SIGNATURES = {
     "ovb_check_device": (C.c_int, []),
     "ovb_launch_count": (C.c_int64, []),
     "ovb_add_launch_count": (None, [C.c_int64]),
+    "ovb_video_to_uint8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                     C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "ovb_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "ovb_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
     "ovb_attn_workspace_size": (C.c_int64, [C.POINTER(AttnArgs)]),

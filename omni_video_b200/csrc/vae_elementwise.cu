@@ -173,6 +173,31 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     p[c] = __float2bfloat16_rn(exp2f((s[c] - m) * scale_log2) * inv);
 }
 
+// Decoded video -> displayable frames (reference utils/utils.py:177-185, `cache_video`):
+//   out[t, y0 + y, x0 + x, c] = uint8( (clamp(x[c, t, y, x], lo, hi) - lo) / max(hi - lo, 1e-5) * 255 )   (truncation)
+// planar fp32 [C, T, H, W] in, interleaved uint8 out with arbitrary frame/row pitch and origin, so that several
+// videos can be laid out as torchvision's make_grid does.  Same fp32 operation order as torch (clamp, sub, div,
+// mul, cast), IEEE division: results are bit-identical.  One thread per pixel; 12 B read, 3 B written per pixel.
+__global__ void video_to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int C, int T, int H,
+                                      int W, long long out_frame_stride, long long out_row_stride, float lo, float hi,
+                                      float denom) {
+  const long long n = static_cast<long long>(T) * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xw = static_cast<int>(i % W);
+    const long long r = i / W;
+    const int y = static_cast<int>(r % H);
+    const int t = static_cast<int>(r / H);
+    uint8_t* o = out + t * out_frame_stride + y * out_row_stride + static_cast<long long>(xw) * C;
+    for (int c = 0; c < C; ++c) {
+      float v = x[c * n + i];
+      v = fminf(fmaxf(v, lo), hi);
+      v = __fmul_rn(__fdiv_rn(__fsub_rn(v, lo), denom), 255.0f);
+      o[c] = static_cast<uint8_t>(static_cast<int>(v));
+    }
+  }
+}
+
 }  // namespace ovb
 
 extern "C" int ovb_rmsnorm_silu_cl(const void* x, const float* gamma, void* out, int64_t n_vox,
@@ -245,6 +270,27 @@ extern "C" int ovb_softmax_rows(const float* S, int64_t lds, void* P, int64_t ld
   OVB_CHECK_ARG(S && P && rows > 0 && cols > 0 && lds >= cols && ldp >= cols, "ovb_softmax_rows: bad arguments");
   softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, cols, scale * 1.4426950408889634f);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_video_to_uint8(const float* x, uint8_t* out, int32_t C, int32_t T, int32_t H, int32_t W,
+                                  int64_t out_frame_stride, int64_t out_row_stride, float lo, float hi,
+                                  void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(x && out, "ovb_video_to_uint8: null pointer");
+  OVB_CHECK_ARG(C >= 1 && C <= 4 && T > 0 && H > 0 && W > 0, "ovb_video_to_uint8: bad shape C=%d T=%d H=%d W=%d", C,
+                T, H, W);
+  OVB_CHECK_ARG(out_row_stride >= static_cast<int64_t>(W) * C && out_frame_stride >= out_row_stride * H,
+                "ovb_video_to_uint8: output pitches too small");
+  OVB_CHECK_ARG(hi >= lo, "ovb_video_to_uint8: value range (%g, %g)", lo, hi);
+  const float denom = fmaxf(hi - lo, 1e-5f);
+  const long long n = static_cast<long long>(T) * H * W;
+  const long long blocks = (n + 255) / 256;
+  const unsigned grid = static_cast<unsigned>(blocks < 148LL * 32 ? blocks : 148LL * 32);
+  video_to_uint8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, C, T, H, W, out_frame_stride,
+                                                                             out_row_stride, lo, hi, denom);
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OVB_OK;
