@@ -29,7 +29,7 @@ from __future__ import annotations
 
 import logging
 import math
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.nn as nn

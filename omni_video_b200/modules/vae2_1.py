@@ -34,7 +34,7 @@ import torch.nn as nn
 
 from .. import ops, vae_ops
 from ..ops import EPI_BF16, EPI_F32, EPI_RESID_BF16
-from ..vae_ops import CONV_OUT_BF16, CONV_OUT_F32_PLANAR_CLAMP
+from ..vae_ops import CONV_OUT_F32_PLANAR_CLAMP
 
 __all__ = ["Wan2_1_VAE", "WanVAE_", "VAEEngine"]
 

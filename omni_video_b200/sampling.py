@@ -25,7 +25,7 @@ are batched or not (2 draws per sample per call: 4 per step either way).
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 

@@ -10,7 +10,7 @@ the output would be identically zero (SURVEY.md §8(c) "Random-init pitfalls").
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Tuple
+from typing import Dict, Tuple
 
 import numpy as np
 import torch

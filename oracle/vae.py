@@ -26,7 +26,7 @@ from __future__ import annotations
 
 import math
 import re
-from typing import Dict, List
+from typing import Dict
 
 import torch
 import torch.nn.functional as F
