@@ -353,6 +353,8 @@ def run_ours(args):
             return
         torch.cuda.synchronize()
         if use_graph:
+            dist.barrier()                      # leave together: rank 0 prints its line before anyone goes
+            torch.cuda.synchronize()
             model._engine._graphs.clear()
             sys.stdout.flush()
             sys.stderr.flush()
