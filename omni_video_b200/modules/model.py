@@ -198,15 +198,20 @@ class DiTEngine:
         import torch.distributed as dist
         return dist.get_rank(group=g)
 
+    @staticmethod
+    def _check_device(dev):
+        """The product has no CPU path: parameters must be on the GPU the kernels run on."""
+        if dev.type != "cuda":
+            raise ops._lib.OvbError("WanModel parameters must live on a CUDA device: the B200 path "
+                                    "has no CPU fallback")
+
     def packed(self) -> _Packed:
         key = self._key()
         if self._packed is not None and key == self._packed_key:
             return self._packed
         m = self.m
         dev = m.patch_embedding.weight.device
-        if dev.type != "cuda":
-            raise ops._lib.OvbError("WanModel parameters must live on a CUDA device: the B200 path "
-                                    "has no CPU fallback")
+        self._check_device(dev)
         P = _Packed()
         sp = self.sp_size()
         d, h = m.dim, m.num_heads
