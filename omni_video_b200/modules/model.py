@@ -339,7 +339,7 @@ class DiTEngine:
         What that buys is the launch gaps: nothing at 32760 tokens on one GPU, several per cent when
         sequence parallelism cuts every kernel to a fraction of a millisecond."""
         if (not self.use_graph() or not x[0].is_cuda or t.dim() != 1 or ops.timeline_active()
-                or torch.cuda.is_current_stream_capturing()):
+                or torch.cuda.is_current_stream_capturing() or (self.sp_size() > 1 and len(x) != 1)):
             return self._forward(x, t, context, seq_len, y)
         sig = (tuple((tuple(u.shape), u.dtype) for u in x), tuple(t.shape), t.dtype,
                tuple((tuple(c.shape), c.dtype) for c in context), seq_len,
@@ -354,7 +354,10 @@ class DiTEngine:
 
     @torch.no_grad()
     def _forward(self, x: List[torch.Tensor], t: torch.Tensor, context: List[torch.Tensor],
-                 seq_len: int, y: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+                 seq_len: int, y: Optional[List[torch.Tensor]] = None, finish: bool = True):
+        """finish=False stops after the head projection and returns (head output of this rank's rows,
+        grids): the part a CUDA graph captures.  What follows (`_finish`) holds the forward's only NCCL
+        collective and is always run eagerly."""
         m = self.m
         if m.model_type == "i2v":
             assert y is not None
@@ -368,6 +371,7 @@ class DiTEngine:
         if sp > 1 and B != 1:
             # the reference pipeline always calls with one sample per forward (x2x_gen_unified.py
             # :480-481); run samples one after another under sequence parallelism
+            assert finish, "batched sequence-parallel forwards are not captured"
             out = []
             for i in range(B):
                 out += self._forward([x[i]], t[i:i + 1], [context[i]], seq_len, None)
@@ -480,19 +484,29 @@ class DiTEngine:
         hn = ops.layernorm_modulate(xres, hm[:, 1], hm[:, 0], eps, rows_per_sample=s_loc,
                                     out_dtype=f32)
         yout = ops.linear_f32(hn, P.head_w, P.head_b)            # [M, 4*out_dim] fp32
+        if not finish:
+            return yout, grids
+        return self._finish(yout, grids, seq_len)
+
+    @torch.no_grad()
+    def _finish(self, yout: torch.Tensor, grids, seq_len: int) -> List[torch.Tensor]:
+        """Gather the head output of all sequence-parallel ranks (the forward's one NCCL collective) and
+        unpatchify (reference model.py:526-549)."""
+        sp = self.sp_size()
         if sp > 1:
             import torch.distributed as dist
-            full = torch.empty((sp, M, yout.shape[1]), device=dev, dtype=f32)
+            M = yout.shape[0]
+            full = torch.empty((sp, M, yout.shape[1]), device=yout.device, dtype=f32)
             dist.all_gather_into_tensor(full, yout.contiguous(), group=self.sp_group())
             yout = full.view(sp * M, -1)                         # B == 1: rows are in token order
-        outs = []
-        for b in range(B):
-            outs.append(ops.unpatchify(yout[b * seq_len:(b + 1) * seq_len], m.out_dim, grids[b]))
-        return outs
+        return [ops.unpatchify(yout[b * seq_len:(b + 1) * seq_len], self.m.out_dim, grids[b])
+                for b in range(len(grids))]
 
 
 class _GraphedForward:
-    """One captured DiT forward: static input buffers, a CUDA graph, static outputs."""
+    """One captured DiT forward: static input buffers, a CUDA graph of everything up to the head projection
+    (no NCCL inside: under sequence parallelism the exchanges are peer stores + flag barriers), and the eager
+    tail (`DiTEngine._finish`: gather of the head output, unpatchify)."""
 
     def __init__(self, eng: DiTEngine, x, t, context, seq_len, y):
         dev = x[0].device
@@ -511,8 +525,9 @@ class _GraphedForward:
         n0 = _lib_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = eng._forward(self.x, self.t, self.ctx, seq_len, self.y)
+            self.yout, self.grids = eng._forward(self.x, self.t, self.ctx, seq_len, self.y, finish=False)
         self.launches = _lib_launch_count() - n0   # kernels of this library inside one replay
+        self.eng, self.seq_len = eng, seq_len
 
     def __call__(self, x, t, context, y):
         for dst, src in zip(self.x, x):
@@ -525,7 +540,7 @@ class _GraphedForward:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         ops.add_launch_count(self.launches)
-        return [o.clone() for o in self.out]
+        return self.eng._finish(self.yout, self.grids, self.seq_len)
 
 
 def _lib_launch_count() -> int:
