@@ -82,6 +82,22 @@ def _sp_worker(rank, world, port, results):
         out = model(xs, t=t, context=ctx, seq_len=seq_len)[0]
         err = O.rel_l2(out, ref)
         assert out.shape == ref.shape and err <= 1e-3, err
+        # the reference's own integration idiom (x2x_gen_unified.py:171-182): per-module hooks rebound with
+        # types.MethodType; context sequence-sharded, four all-to-alls per attention
+        import types
+        from omni_video_b200.distributed import ulysses
+        from omni_video_b200.distributed.full_sequence_parallel import (sp_attn_forward, sp_cross_attn_forward,
+                                                                        sp_dit_forward)
+        mpatch.setattr(ulysses, "flash_attention",
+                       lambda q, k, v, k_lens=None, window_size=(-1, -1), **kw: cpu_emulation.attention(q, k, v, k_lens=k_lens))
+        for blk in model.blocks:
+            blk.self_attn.sp_group = blk.cross_attn.sp_group = model.sp_group
+            blk.self_attn.forward = types.MethodType(sp_attn_forward, blk.self_attn)
+            blk.cross_attn.forward = types.MethodType(sp_cross_attn_forward, blk.cross_attn)
+        model.forward = types.MethodType(sp_dit_forward, model)
+        hooks = model(xs, t=t, context=ctx, seq_len=seq_len)[0]
+        err = O.rel_l2(hooks, ref)
+        assert hooks.shape == ref.shape and err <= 5e-3, err
         results[rank] = "ok"
         mpatch.undo()
     except Exception as ex:  # pragma: no cover
