@@ -123,3 +123,28 @@ def test_product_refuses_cpu_parameters_without_the_emulation():
     xs, t, ctx = synth.dit_inputs(cfg, (2, 4, 4), 5, seed=1)
     with pytest.raises(OvbError, match="no CPU fallback"):
         _model(cfg, synth.dit_state_dict(cfg, seed=1))(xs, t=t, context=ctx, seq_len=8)
+
+
+def test_patch_seam_on_the_reference_own_class(monkeypatch):
+    """Build container only (skipped where /root/reference is absent): the REFERENCE's `WanModel` instance,
+    its forward rebound by `patch.patch_reference_model`, gives — with emulated kernels — what its own
+    forward gave (the golden); i.e. attribute names, parameter tree and call convention line up with the
+    real class, not just with our mirror of it."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    from omni_video_b200 import patch
+    cpu_emulation.install(monkeypatch)
+    ref = ref_loader.load_reference(cpu_attention=True)
+    meta, gold = load_golden("dit_tiny_pad")
+    cfg, sd, xs, t, ctx, seq_len = dit_case(meta)
+    model = ref.model.WanModel(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(bf16).eval().requires_grad_(False)
+    assert type(model).__module__ == "omnivideo.modules.model"
+    patch.patch_reference_model(model)
+    out = model(xs, t=t, context=[c.to(bf16) for c in ctx], seq_len=seq_len)
+    assert isinstance(out, list) and out[0].dtype == torch.float32 and out[0].shape == gold[0].shape
+    assert O.rel_l2(out[0], gold[0]) <= 1e-2
+    patch.unpatch_reference_model(model)
+    assert "forward" not in vars(model)

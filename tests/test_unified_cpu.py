@@ -117,3 +117,32 @@ def test_patch_reference_unified_binds_every_method_the_forward_needs():
     assert out is seen["ctx"] and O.rel_l2(out[0].float(), gold[0]) <= 5e-3
     with pytest.raises(TypeError):
         patch.patch_reference_unified(nn.Linear(2, 2))
+
+
+def test_patch_seam_on_the_reference_own_unified_class():
+    """Build container only: the REFERENCE's `UnifiedWanWithMixedConditionModel` instance after
+    `patch.patch_reference_unified`, with the two CUDA pieces replaced by the oracle's arithmetic, builds the
+    context its own forward built (the golden) — names and conventions line up with the real class."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    from omni_video_b200 import patch
+    ref_loader.load_reference(cpu_attention=True)
+    ref_loader._load("omnivideo.modules.visual_context_adapter", "omnivideo/modules/visual_context_adapter.py")
+    ref_unified = ref_loader._load("omnivideo.modules.unified_model", "omnivideo/modules/unified_model.py")
+    meta, gold = load_golden("unified_full")
+    cfg, sd, ar, ctx, vis, st = unified_case(meta)
+    r = ref_unified.UnifiedWanWithMixedConditionModel(
+        wan_config=dict(cfg), vlm_in_dim=meta["vlm_in_dim"], use_visual_context_adapter=True,
+        visual_context_adapter_patch_size=tuple(meta["patch"]), max_context_len=meta["max_len"], skip_init=True)
+    r.load_state_dict(sd, strict=False)
+    assert type(r).__module__ == "omnivideo.modules.unified_model"
+    patch.patch_reference_unified(r)
+    sd32 = {k: v.float() for k, v in sd.items()}
+    r._vlm = types.MethodType(lambda self, tokens: U.vlm_features(sd32, tokens.float(), 1e-6), r)
+    r.visual_context_adapter.forward = lambda x: U.visual_context(sd32, x.float(), 1e-6).unsqueeze(0)
+    seen = {}
+    r.wan_model.forward = lambda x, t=None, context=None, seq_len=None: seen.setdefault("ctx", context)
+    out = r([torch.zeros(16, 1, 2, 2)], t=torch.zeros(1), context=ctx, ar_vision_input=ar, visual_emb=vis, seq_len=1,
+            special_token_dict=st, classifier_free_ratio=0.0, unconditioned_context=None, condition_mode="full")
+    assert out is seen["ctx"] and O.rel_l2(out[0].float(), gold[0]) <= 5e-3
