@@ -19,9 +19,16 @@ pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tr
 @pytest.mark.parametrize("module,prefix", [("oracle.gen_golden_unified", "unified_"), ("oracle.gen_golden_t5", "t5_"),
                                            ("oracle.gen_golden_video", "video_"), ("oracle.gen_golden_unipc", "unipc_")])
 def test_generator_reproduces_committed_fixtures(tmp_path, monkeypatch, module, prefix):
+    import sys
     gen = importlib.import_module(module)
     monkeypatch.setattr(gen, "GOLDEN_DIR", str(tmp_path))
-    gen.main()
+    before = set(sys.modules)
+    try:
+        gen.main()
+    finally:                      # the generators register stand-ins (imageio, tokenizers): do not leak them
+        for name in ("imageio", "omnivideo.modules.tokenizers"):
+            if name in sys.modules and name not in before:
+                del sys.modules[name]
     made = sorted(glob.glob(os.path.join(str(tmp_path), prefix + "*.npz")))
     committed = sorted(glob.glob(os.path.join(GOLDEN_DIR, prefix + "*.npz")))
     assert [os.path.basename(p) for p in made] == [os.path.basename(p) for p in committed] and made
