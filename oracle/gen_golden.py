@@ -47,10 +47,38 @@ def run_dit_case(ref, case):
     return cfg, seq_len, [o.numpy() for o in out]
 
 
+# image-to-video flavour (model.py:417-424, :446-447): `y` is concatenated to `x` along the channels before
+# the patch embedding, `model_type='i2v'` makes it mandatory
+I2V_CASE = dict(name="dit_tiny_i2v", cfg=dict(model_type="i2v", in_dim=20), grid=(2, 6, 8), ctx_len=9, y_channels=4,
+                t=640)
+
+
+def run_i2v_case(ref):
+    case = I2V_CASE
+    cfg = dict(synth.TINY_DIT)
+    cfg.update(case["cfg"])
+    model = ref.model.WanModel(**cfg)
+    model.load_state_dict(synth.dit_state_dict(cfg, seed=1818), strict=True)
+    model.eval().requires_grad_(False)
+    xs, t, ctx = synth.dit_inputs(cfg, case["grid"], case["ctx_len"], seed=7, batch=1, timestep=case["t"])
+    nx = cfg["in_dim"] - case["y_channels"]
+    Fr, H, W = case["grid"]
+    seq_len = Fr * (H // 2) * (W // 2)
+    with torch.no_grad():
+        out = model([u[:nx] for u in xs], t=t, context=ctx, seq_len=seq_len, y=[u[nx:] for u in xs])
+    meta = dict(kind="dit_forward_i2v", cfg=cfg, grid=case["grid"], ctx_len=case["ctx_len"], seq_len=seq_len, batch=1,
+                t=case["t"], y_channels=case["y_channels"], weight_seed=1818, input_seed=7,
+                reference="omnivideo/modules/model.py WanModel.forward with y (model_type i2v), fp32 CPU")
+    path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+    np.savez_compressed(path, meta=json.dumps(meta), out0=out[0].numpy())
+    print(f"wrote {path}: out0 shape {tuple(out[0].shape)} absmax {out[0].abs().max():.4f}")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = ref_loader.load_reference(cpu_attention=True)
+    run_i2v_case(ref)
     for case in DIT_CASES:
         cfg, seq_len, outs = run_dit_case(ref, case)
         meta = dict(kind="dit_forward", cfg=cfg, grid=case["grid"], ctx_len=case["ctx_len"],

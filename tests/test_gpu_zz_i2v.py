@@ -1,0 +1,24 @@
+"""`WanModel.forward(..., y=...)` (model_type 'i2v', reference model.py:417-424, :446-447) on the GPU against the
+reference's own output.  The path is `torch.cat` in front of kernels that are parity-green, its host side is
+covered on CPU (tests/test_i2v_cpu.py); this file was added after the round's GPU budget was spent and had not run
+on a B200 when committed — `xfail(strict=False)` until it has (a pass is reported as XPASS)."""
+import pytest
+import torch
+
+from oracle import dit as O
+from tests.test_i2v_cpu import i2v_case
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120),
+              pytest.mark.xfail(strict=False, reason="first GPU run pending (written after the round's GPU budget)")]
+
+
+def test_i2v_forward_vs_reference_golden():
+    from omni_video_b200.modules.model import WanModel
+    cfg, sd, x, y, xcat, t, ctx, seq_len, gold = i2v_case()
+    with torch.device("cuda"):
+        m = WanModel(**cfg, skip_init=True)
+    m.load_state_dict({k: v.cuda() for k, v in sd.items()}, strict=True)
+    m = m.to(torch.bfloat16).eval().requires_grad_(False)
+    out = m([u.cuda() for u in x], t=t.cuda(), context=[c.cuda().to(torch.bfloat16) for c in ctx], seq_len=seq_len,
+            y=[u.cuda() for u in y])[0]
+    assert out.shape == gold.shape and O.rel_l2(out.cpu(), gold) <= 1e-2
