@@ -406,8 +406,8 @@ class DiTEngine:
             else:
                 qkv_recv, att_recv = tr.qkv_recv, tr.att_recv
         grid0 = grids[0]
-        if B > 1:
-            assert all(g == grid0 for g in grids), "batched samples must share one latent grid"
+        same_grid = all(g == grid0 for g in grids)      # a ragged batch (reference model.py:455-464 pads every
+        #                                                 sample to seq_len) rotates each sample with its own grid
 
         for li, W in enumerate(P.blocks):
             mb = mod[li]  # [B, 6, d]: shift_sa, scale_sa, gate_sa, shift_ffn, scale_ffn, gate_ffn
@@ -417,11 +417,18 @@ class DiTEngine:
             if sp == 1:
                 ops.gemm(hbuf, W.qkv_w, W.qkv_b, epilogue=EPI_BF16, out=qkv)
                 q2, k2 = qkv[:, :d], qkv[:, d:2 * d]
-                if W.nq_w is not None:
+                if W.nq_w is not None and same_grid:
                     ops.rmsnorm_rope_(q2, W.nq_w, eps, cs_table=self._cs_table, grid=grid0,
                                       rows_per_sample=s_loc)
                     ops.rmsnorm_rope_(k2, W.nk_w, eps, cs_table=self._cs_table, grid=grid0,
                                       rows_per_sample=s_loc)
+                elif W.nq_w is not None:
+                    for b in range(B):
+                        rows = slice(b * s_loc, (b + 1) * s_loc)
+                        ops.rmsnorm_rope_(q2[rows], W.nq_w, eps, cs_table=self._cs_table, grid=grids[b],
+                                          rows_per_sample=s_loc)
+                        ops.rmsnorm_rope_(k2[rows], W.nk_w, eps, cs_table=self._cs_table, grid=grids[b],
+                                          rows_per_sample=s_loc)
                 else:
                     raise NotImplementedError("qk_norm=False is not on the Omni-Video hot path")
                 q4 = qkv.view(B, s_loc, 3, h, 128)

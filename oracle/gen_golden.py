@@ -74,11 +74,33 @@ def run_i2v_case(ref):
     print(f"wrote {path}: out0 shape {tuple(out[0].shape)} absmax {out[0].abs().max():.4f}")
 
 
+def run_ragged_case(ref):
+    """Two samples with DIFFERENT latent grids in one call: every sample is zero-padded to seq_len
+    (model.py:455-464), attends to its own tokens only and is rotated with its own (f, h, w)."""
+    cfg = dict(synth.TINY_DIT)
+    model = ref.model.WanModel(**cfg)
+    model.load_state_dict(synth.dit_state_dict(cfg, seed=1818), strict=True)
+    model.eval().requires_grad_(False)
+    grids = [(2, 6, 8), (3, 4, 4)]                       # 24 and 12 tokens
+    xa, t, ctx_a = synth.dit_inputs(cfg, grids[0], 9, seed=7, batch=1, timestep=321)
+    xb, _, ctx_b = synth.dit_inputs(cfg, grids[1], 17, seed=8, batch=1, timestep=321)
+    seq_len = 28
+    with torch.no_grad():
+        out = model(xa + xb, t=torch.cat([t, t]), context=ctx_a + ctx_b, seq_len=seq_len)
+    meta = dict(kind="dit_forward_ragged", cfg=cfg, grids=grids, ctx_lens=[9, 17], seq_len=seq_len, t=321,
+                weight_seed=1818, input_seeds=[7, 8],
+                reference="omnivideo/modules/model.py WanModel.forward on a batch of two different grids, fp32 CPU")
+    path = os.path.join(GOLDEN_DIR, "dit_tiny_ragged.npz")
+    np.savez_compressed(path, meta=json.dumps(meta), out0=out[0].numpy(), out1=out[1].numpy())
+    print(f"wrote {path}: shapes {[tuple(o.shape) for o in out]}")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = ref_loader.load_reference(cpu_attention=True)
     run_i2v_case(ref)
+    run_ragged_case(ref)
     for case in DIT_CASES:
         cfg, seq_len, outs = run_dit_case(ref, case)
         meta = dict(kind="dit_forward", cfg=cfg, grid=case["grid"], ctx_len=case["ctx_len"],

@@ -22,3 +22,17 @@ def test_i2v_forward_vs_reference_golden():
     out = m([u.cuda() for u in x], t=t.cuda(), context=[c.cuda().to(torch.bfloat16) for c in ctx], seq_len=seq_len,
             y=[u.cuda() for u in y])[0]
     assert out.shape == gold.shape and O.rel_l2(out.cpu(), gold) <= 1e-2
+
+
+def test_ragged_batch_forward_vs_reference_golden():
+    """Two samples with different latent grids in one call (tests/test_ragged_batch_cpu.py has the CPU side)."""
+    from omni_video_b200.modules.model import WanModel
+    from tests.test_ragged_batch_cpu import ragged_case
+    cfg, sd, xs, t, ctx, seq_len, gold = ragged_case()
+    with torch.device("cuda"):
+        m = WanModel(**cfg, skip_init=True)
+    m.load_state_dict({k: v.cuda() for k, v in sd.items()}, strict=True)
+    m = m.to(torch.bfloat16).eval().requires_grad_(False)
+    outs = m([u.cuda() for u in xs], t=t.cuda(), context=[c.cuda().to(torch.bfloat16) for c in ctx], seq_len=seq_len)
+    for o, g in zip(outs, gold):
+        assert o.shape == g.shape and O.rel_l2(o.cpu(), g) <= 1e-2
