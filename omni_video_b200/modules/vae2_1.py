@@ -328,6 +328,13 @@ class VAEEngine:
         if self.strip is not None and self.strip.p == 1:
             self.strip = None
 
+    @staticmethod
+    def _check_device(dev):
+        """The product has no CPU path: parameters must be on the GPU the kernels run on."""
+        if dev.type != "cuda":
+            raise ops._lib.OvbError("VAE parameters must live on a CUDA device: the B200 path has "
+                                    "no CPU fallback")
+
     # -------------------------------------------------------------------------------- weights
     def _params(self) -> Dict[str, torch.Tensor]:
         key = tuple((p.device, p._version, p.data_ptr()) for p in self.m.parameters())
@@ -335,9 +342,7 @@ class VAEEngine:
             self._packed, self._key = {}, key
             self._sd = {k: v for k, v in self.m.state_dict().items()}
             dev = next(self.m.parameters()).device
-            if dev.type != "cuda":
-                raise ops._lib.OvbError("VAE parameters must live on a CUDA device: the B200 path has "
-                                        "no CPU fallback")
+            self._check_device(dev)
             self.dev = dev
             z = self.mean_host.numel()
             self.mean, self.std = self.mean_host.to(dev), self.std_host.to(dev)

@@ -162,3 +162,89 @@ def install(monkeypatch):
                          modulation_table=modulation_table, cast_bf16_to_f32=lambda x: x.float(),
                          cast_f32_to_bf16=lambda x: x.to(bf16)).items():
         monkeypatch.setattr(ops, name, fn)
+
+
+# ------------------------------------------------------------------------------------------------- VAE
+def conv3d(x, pc, out_extent, *, out=None, out_strides=None, out_base=0, n_group=0, group_stride=0, resid=None,
+           out_mode=0, plane_stride=0, dh_shift=0):
+    """ovb_conv3d (include/ovb200.h): taps with zero fill outside x, bias, optional bf16 residual (the conv result
+    is rounded to bf16 before the add), output scattered through (os_t, os_h, os_w, out_base, n_group)."""
+    from omni_video_b200 import vae_ops
+    Ti, Hi, Wi, Cin = x.shape
+    To, Ho, Wo = out_extent
+    st, sh, sw = pc.stride
+    xf = x.float()
+    t = torch.arange(To).view(To, 1, 1)
+    h = torch.arange(Ho).view(1, Ho, 1)
+    w = torch.arange(Wo).view(1, 1, Wo)
+    acc = torch.zeros((To, Ho, Wo, pc.cout), dtype=f32)
+    for k, (dt, dh, dw) in enumerate(pc.taps):
+        ti, hi, wi = t * st + dt, h * sh + dh + dh_shift, w * sw + dw
+        ok = ((ti >= 0) & (ti < Ti)) & ((hi >= 0) & (hi < Hi)) & ((wi >= 0) & (wi < Wi))
+        ti, hi, wi = (ti.clamp(0, Ti - 1).expand(To, Ho, Wo), hi.clamp(0, Hi - 1).expand(To, Ho, Wo),
+                      wi.clamp(0, Wi - 1).expand(To, Ho, Wo))
+        xs = xf[ti, hi, wi] * ok.unsqueeze(-1)
+        acc += xs @ pc.w[:pc.cout, k * Cin:(k + 1) * Cin].float().T
+    if pc.bias is not None:
+        acc += pc.bias.float()
+    n = torch.arange(pc.cout)
+    if out_strides is None:
+        out_strides = (Ho * Wo * pc.cout, Wo * pc.cout, pc.cout)
+    os_t, os_h, os_w = out_strides
+    base = out_base + t * os_t + h * os_h + w * os_w                                   # [To, Ho, Wo]
+    if out_mode == vae_ops.CONV_OUT_BF16:
+        if out is None:
+            out = torch.empty((To, Ho, Wo, pc.cout), dtype=bf16)
+        nmap = (n // n_group) * group_stride + n % n_group if n_group else n
+        idx = (base.unsqueeze(-1) + nmap.view(1, 1, 1, -1)).reshape(-1)
+        y = acc
+        if resid is not None:
+            y = _rb(y) + resid.reshape(-1)[idx].float().view_as(y)
+        out.view(-1)[idx] = y.to(bf16).reshape(-1)
+        return out
+    idx = (base.unsqueeze(-1) + (n * plane_stride).view(1, 1, 1, -1)).reshape(-1)
+    y = acc.clamp(-1.0, 1.0) if out_mode == vae_ops.CONV_OUT_F32_PLANAR_CLAMP else acc
+    out.view(-1)[idx] = y.reshape(-1)
+    return out
+
+
+def rmsnorm_silu(x, gamma, silu=True, out=None):
+    xf = x.float()
+    y = xf / xf.norm(dim=-1, keepdim=True).clamp_min(1e-12) * (x.shape[-1] ** 0.5) * gamma.float()
+    if silu:
+        y = F.silu(y)
+    if out is None:
+        return y.to(bf16)
+    out.copy_(y.to(bf16))
+    return out
+
+
+def planar_to_cl(src, scale, shift, cpad):
+    C = src.shape[0]
+    y = (src * scale.view(-1, 1, 1, 1) + shift.view(-1, 1, 1, 1)).permute(1, 2, 3, 0)
+    out = torch.zeros(y.shape[:3] + (cpad,), dtype=bf16)
+    out[..., :C] = y.to(bf16)
+    return out
+
+
+def cl_to_planar(src, scale, shift, c):
+    return (src[..., :c].float() * scale.view(1, 1, 1, -1) + shift.view(1, 1, 1, -1)).permute(3, 0, 1, 2).contiguous()
+
+
+def softmax_rows(S, scale, out=None):
+    p = torch.softmax(S * scale, dim=-1).to(bf16)
+    if out is None:
+        return p
+    out.copy_(p)
+    return out
+
+
+def install_vae(monkeypatch):
+    """VAE counterpart of install(): `omni_video_b200.vae_ops` entry points + the engine's device check."""
+    from omni_video_b200 import vae_ops
+    from omni_video_b200.modules.vae2_1 import VAEEngine
+    install(monkeypatch)
+    monkeypatch.setattr(VAEEngine, "_check_device", staticmethod(lambda dev: None))
+    for name, fn in dict(conv3d=conv3d, rmsnorm_silu=rmsnorm_silu, planar_to_cl=planar_to_cl, cl_to_planar=cl_to_planar,
+                         softmax_rows=softmax_rows).items():
+        monkeypatch.setattr(vae_ops, name, fn)
