@@ -149,8 +149,11 @@ int ovb_attn_plan(const ovb_attn_args* args, int32_t* n_whole, int32_t* n_tail, 
  * (3) wait until all `world` slots of the own pad hold a value >= epoch.  Epochs must increase by one
  * per call on every rank: with epoch_counter (device uint32, owned by this rank) the kernel uses
  * *epoch_counter + 1 and stores it back, which keeps the launch valid inside a replayed CUDA graph;
- * with epoch_counter == NULL the `epoch` argument is used.  The wait gives up after ~2 s of spinning
- * and sets *status (device uint32, may be NULL) to 1 instead of hanging the GPU. */
+ * with epoch_counter == NULL the `epoch` argument is used.  A wait that is still unsatisfied after
+ * ~30 s (a peer died, or the epochs diverged) is FATAL: the kernel sets *status (device uint32, may
+ * be NULL) to 1 and traps, so the stream never continues into kernels that would read half-written
+ * receive buffers; the host sees a launch failure at its next synchronisation.  Ranks of a group
+ * must therefore stay in lock-step. */
 int ovb_peer_signal_wait(uint32_t* const* peer_pads, int32_t rank, int32_t world, uint32_t epoch,
                          uint32_t* epoch_counter, uint32_t* status, void* stream);
 /* cudaDeviceEnablePeerAccess(peer_device) for the current device ("already enabled" is success). */

@@ -566,16 +566,8 @@ struct AttnSplit {
   int parts;
 };
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
-}
+// SM count of the CURRENT device (a process may drive several GPUs)
+static int sm_count() { return device_sm_count(); }
 
 // One CTA per SM (227 KB of shared memory, all 512 TMEM columns), equal-cost items: T items take
 // ceil(T / SMs) rounds.  When the last round is mostly empty, its r items are cut g ways along the
@@ -730,12 +722,10 @@ extern "C" int ovb_attn_fwd(const ovb_attn_args* a, void* stream) {
     p.ws_ml = reinterpret_cast<float2*>(p.ws_o + ctas * 256 * 128);
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    OVB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  if (once_per_device(attr_set))
+    OVB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kAttnSmem));
   const int grid = sp.n_whole + sp.n_tail * sp.parts;
   attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   OVB_CHECK_CUDA(cudaGetLastError());

@@ -504,12 +504,11 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
   }
 
   const int smem_bytes = p.stages * p.stage_bytes + kConvStagingBytes + 1024 + 512;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (once_per_device(attr_set)) {
     OVB_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kConvSmemBudget + 2048));
-    attr_set = true;
   }
   const long long m_tiles = static_cast<long long>(p.To) * p.n_ht * p.n_wt;
   const long long num_tiles = ((m_tiles + 1) / 2) * p.n_nt;  // pair tiles

@@ -880,9 +880,15 @@ __global__ void peer_signal_wait_kernel(const PeerPads pads, int rank, int world
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
       if (v >= epoch) break;
-      if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died or the epochs diverged
-        if (status != nullptr) *status = 1u;
-        break;
+      // ~30 s at 2 GHz: a peer died or the epochs diverged.  Continuing would let the next kernel
+      // read half-written receive buffers, so this is FATAL: record the reason and trap (the host
+      // sees a launch failure at its next synchronisation; UlyssesPeerTransport.check() names it).
+      if (clock64() - t0 > 60000000000LL) {
+        if (status != nullptr) {
+          *status = 1u;
+          __threadfence_system();
+        }
+        __trap();
       }
     } while (true);
   }

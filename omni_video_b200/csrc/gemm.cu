@@ -644,15 +644,14 @@ extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
   p.num_m_tiles = (a->M + 2 * kBM - 1) / (2 * kBM);
   p.num_n_tiles = (a->N + kBN - 1) / kBN;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (once_per_device(attr_set)) {
     OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_RESID_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_GATE_RESID_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<OVB_EPI_RESID_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-    attr_set = true;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = device_sm_count();
@@ -673,11 +672,10 @@ extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
     if (rc != OVB_OK) return rc;
     rc = encode_tmap_f32(&tmO, a->out, 2, dims, os, box);
     if (rc != OVB_OK) return rc;
-    static bool attr2 = false;
-    if (!attr2) {
+    static bool attr2[64] = {};
+    if (once_per_device(attr2)) {
       OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_resid_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmResidSmem));
       OVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_resid_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmResidSmem));
-      attr2 = true;
     }
     if (a->epilogue == OVB_EPI_GATE_RESID_F32)
       gemm_resid_tma_kernel<true><<<grid, kGemmThreads, kGemmResidSmem, st>>>(tmA, tmB, tmR, tmO, p);

@@ -126,6 +126,14 @@ int encode_tmap_f32(CUtensorMap* out, const void* gptr, int rank, const uint64_t
   return OVB_OK;
 }
 
+bool once_per_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;  // unknown: redo the setup
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 int device_sm_count() {
   static int sms[64] = {0};
   int dev = 0;

@@ -46,6 +46,9 @@ int encode_tmap_f32(CUtensorMap* out, const void* gptr, int rank, const uint64_t
                     const uint64_t* strides_bytes, const uint32_t* box);
 
 int device_sm_count();
+// true the first time it is called for the CURRENT device with this flag array: per-device one-time
+// setup (cudaFuncSetAttribute is per device; a process may drive several GPUs)
+bool once_per_device(bool (&done)[64]);
 void count_launch();
 
 }  // namespace ovb

@@ -76,6 +76,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe.  Issue it EARLY and consume the result late: the ~100-150 cycle round trip of
+// the probe then overlaps whatever the thread issues in between (a tcgen05.mma issuer must never sit
+// idle behind a barrier instruction: the MMA queue holds only a couple of instructions).
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded spin: a protocol bug must surface as a trap (-> CUDA error on the host), never as a
 // hang of the GPU box.  2^28 polls of a HW-sleeping try_wait is far beyond any legitimate wait.
 // Build with -DOVB_DEBUG_SYNC to get a printf naming the barrier before the trap.
@@ -89,6 +103,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
       __trap();
     }
+  }
+}
+
+// Busy poll with the non-suspending probe: for the ONE thread whose reaction time is on the kernel's
+// critical path (the tcgen05.mma issuer).  A suspended try_wait was measured to resume ~400 cycles
+// after the phase completed; a probe round trip is ~150.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
   }
 }
 
@@ -160,6 +184,17 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
       "r"(c4)
+      : "memory");
+}
+
+// Multicast form: the box lands at the same CTA-relative offset in the shared memory of every CTA
+// of `cta_mask`, and each of those CTAs' mbarrier (same offset) receives the transaction bytes.
+__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                                  int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
       : "memory");
 }
 
@@ -341,6 +376,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// 1-CTA MMAs, but the arrival is multicast: the mbarrier at the same shared-memory offset in every
+// CTA of `cta_mask` receives one arrival (used where two CTAs share a multicast-loaded stage).
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
+          "r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM <-> registers
 // 32x32b: lane i of the warp reads/writes TMEM lane (base_lane + i), N consecutive 32-bit columns.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -396,6 +441,9 @@ __device__ __forceinline__ void tmem_wait_ld() {
 __device__ __forceinline__ void reg_fence32(float* r) {
   asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]), "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]), "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]), "+f"(r[23]), "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]), "+f"(r[30]), "+f"(r[31]));
 }
+__device__ __forceinline__ void reg_fence32u(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
 __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
 }
@@ -421,6 +469,18 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
+// `volatile` forms: the compiler keeps volatile asm statements in source order, which is how the
+// softmax pass software-pipelines its MUFU stream by hand (consumers one chunk behind the producers).
+__device__ __forceinline__ float fast_exp2_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_v(float lo, float hi) {
+  uint32_t r;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 process two fp32 lanes per instruction).
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
@@ -439,6 +499,17 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+__device__ __forceinline__ uint64_t fadd2_v(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("add.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmax2(uint64_t a, uint64_t b) {
+  float a0, a1, b0, b1;
+  unpack_f32x2(a, a0, a1);
+  unpack_f32x2(b, b0, b1);
+  return pack_f32x2(fmaxf(a0, b0), fmaxf(a1, b1));
 }
 __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   uint64_t d;

@@ -45,35 +45,60 @@ def _enable_peer_access(devices):
 
 
 class _Symmetric:
-    """`nbytes` of device memory on every rank of `group`, mapped into every rank."""
+    """`nbytes` of device memory on every rank of `group`, mapped into every rank.
+
+    Construction is split in two so that a failure on ONE rank can never leave the others inside a
+    collective: `allocate()` is purely local (allocate + export), `exchange()` holds the collectives
+    (rendezvous / all_gather_object) and is entered only after every rank has reported a successful
+    `allocate()` (see `_make_symmetric`)."""
 
     def __init__(self, nbytes: int, device: torch.device, group, how: str):
-        self.group, self.how = group, how
+        if how not in ("symm_mem", "ipc"):
+            raise ValueError(how)
+        self.nbytes, self.device, self.group, self.how = nbytes, device, group, how
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        if how == "symm_mem":
+
+    def allocate(self):
+        if self.how == "symm_mem":
             import torch.distributed._symmetric_memory as symm_mem
-            self.local = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
-            self._hdl = symm_mem.rendezvous(self.local, group=group)
-            self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
-        elif how == "ipc":
+            self._symm_mem = symm_mem
+            self.local = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        else:
             # an ordinary cudaMalloc block of its own (not a slice of a cached segment shared with
             # other tensors), exported as a CUDA IPC handle
-            self.local = torch.empty(max(nbytes, 2 << 20), dtype=torch.uint8, device=device)
-            meta = self.local.untyped_storage()._share_cuda_()
-            metas = [None] * self.world
-            dist.all_gather_object(metas, meta, group=group)
-            self._keep, self.ptrs = [], []
-            for r, m in enumerate(metas):
-                if r == self.rank:
-                    self.ptrs.append(self.local.data_ptr())
-                    continue
-                st = torch.UntypedStorage._new_shared_cuda(*m)
-                self._keep.append(st)
-                self.ptrs.append(st.data_ptr())
-            _enable_peer_access({m[0] for r, m in enumerate(metas) if r != self.rank})
+            self.local = torch.empty(max(self.nbytes, 2 << 20), dtype=torch.uint8, device=self.device)
+            self._meta = self.local.untyped_storage()._share_cuda_()
+
+    def exchange(self):
+        """Collective part.  Returns None or the exception of the local, post-collective step (opening
+        the peers' handles), which the caller again agrees on across ranks."""
+        if self.how == "symm_mem":
+            self._hdl = self._symm_mem.rendezvous(self.local, group=self.group)
+            self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
         else:
-            raise ValueError(how)
-        assert self.ptrs[self.rank] == self.local.data_ptr(), "own mapping differs from the local pointer"
+            metas = [None] * self.world
+            dist.all_gather_object(metas, self._meta, group=self.group)
+            try:
+                self._keep, self.ptrs = [], []
+                for r, m in enumerate(metas):
+                    if r == self.rank:
+                        self.ptrs.append(self.local.data_ptr())
+                        continue
+                    st = torch.UntypedStorage._new_shared_cuda(*m)
+                    self._keep.append(st)
+                    self.ptrs.append(st.data_ptr())
+                _enable_peer_access({m[0] for r, m in enumerate(metas) if r != self.rank})
+            except Exception as ex:  # noqa: BLE001
+                return ex
+        if self.ptrs[self.rank] != self.local.data_ptr():
+            return RuntimeError("own mapping differs from the local pointer")
+        return None
+
+
+def _all_ok(ok: bool, device, group) -> bool:
+    flag = torch.full((1,), 1 if ok else 0, device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return int(flag.item()) == 1
 
 
 def _make_symmetric(nbytes, device, group) -> _Symmetric:
@@ -81,16 +106,21 @@ def _make_symmetric(nbytes, device, group) -> _Symmetric:
     errs = []
     for how in order:
         how = how.strip()
-        ok = torch.zeros(1, device=device, dtype=torch.int32)
-        try:
+        s, err = None, None
+        try:                                    # local phase: no collective inside
             s = _Symmetric(nbytes, device, group, how)
-            ok += 1
+            s.allocate()
         except Exception as ex:  # noqa: BLE001 - every rank must agree on the outcome below
-            errs.append(f"{how}: {type(ex).__name__}: {ex}")
-            s = None
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 1:
+            err = ex
+        if not _all_ok(err is None, device, group):
+            errs.append(f"{how} (allocate): {type(err).__name__ if err else 'peer rank'}: {err}")
+            continue
+        # exchange phase: every rank enters the same collectives; a backend whose collective itself
+        # raises on one rank only cannot be recovered from and propagates
+        err = s.exchange()
+        if _all_ok(err is None, device, group):
             return s
+        errs.append(f"{how} (exchange): {type(err).__name__ if err else 'peer rank'}: {err}")
     raise PeerUnavailable("no peer-memory backend worked on every rank: " + " | ".join(errs))
 
 
@@ -129,8 +159,15 @@ class UlyssesPeerTransport:
         ops.peer_signal_wait(self.pad_ptrs, self.rank, self.state)
 
     def check(self):
-        """Raise if any barrier timed out (call outside the timed region: it synchronises)."""
-        if int(self.state[1].item()) != 0:
+        """Raise if any barrier timed out (call outside the timed region: it synchronises).
+        A time-out (a rank more than ~30 s behind, or dead) is fatal on the device as well: the barrier
+        kernel traps after recording it here, so ranks of a group must stay in lock-step."""
+        try:
+            bad = int(self.state[1].item()) != 0
+        except RuntimeError as ex:              # the trap surfaces as a launch failure at this sync
+            raise RuntimeError("peer barrier timed out (device trap): a rank of the sequence-parallel "
+                               "group fell behind by more than ~30 s or died") from ex
+        if bad:
             raise RuntimeError("peer barrier timed out: a rank of the sequence-parallel group fell behind or died")
 
 

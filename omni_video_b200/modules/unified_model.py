@@ -64,6 +64,19 @@ def _ident(t):
     return t
 
 
+def _tensors(t, out):
+    """Flat list of the tensors inside a condition argument, in `_ident`'s traversal order."""
+    if isinstance(t, (list, tuple)):
+        for u in t:
+            _tensors(u, out)
+    elif isinstance(t, dict):
+        for _, v in sorted(t.items()):
+            _tensors(v, out)
+    elif isinstance(t, torch.Tensor):
+        out.append(t)
+    return out
+
+
 # WanModel constructor defaults the reference applies when a key is missing from `wan_config`
 # (unified_model.py:50-61); the remaining keys are forwarded only when present (:63-67).
 _WAN_CONFIG_DEFAULTS = dict(patch_size=(1, 2, 2), dim=2048, ffn_dim=8192, freq_dim=256, num_heads=16,
@@ -157,10 +170,15 @@ class UnifiedWanWithMixedConditionModel(nn.Module):
         them to bf16 under autocast before its first GEMM — the values that reach the GEMM are the same.)"""
         key = (batch_size, _ident(context), _ident(ar_vision_input), _ident(visual_emb),
                _ident(special_token_dict), self._params_key(), self.max_context_len)
+        # `_ident` keys on storage address + version, which identifies a tensor only while it is
+        # alive: a freed condition tensor's block is handed to the next prompt's tensor of the same
+        # size by the caching allocator.  Every entry therefore HOLDS its input tensors (their
+        # addresses cannot be recycled while the entry lives) and a hit is confirmed object by object.
+        inputs = _tensors((context, ar_vision_input, visual_emb, special_token_dict), [])
         hit = self._ctx_cache.get(key)
-        if hit is not None:
+        if hit is not None and len(hit[1]) == len(inputs) and all(a is b for a, b in zip(hit[1], inputs)):
             self.context_cache_hits += 1
-            return hit
+            return hit[0]
         self.context_cache_misses += 1
 
         vlm = self._per_sample(self._vlm, ar_vision_input, batch_size)
@@ -197,8 +215,13 @@ class UnifiedWanWithMixedConditionModel(nn.Module):
             mixed.append(rows[:self.max_context_len] if self.max_context_len is not None else rows)
         if len(self._ctx_cache) >= 8:          # two entries per prompt (cond / uncond) are live at a time
             self._ctx_cache.pop(next(iter(self._ctx_cache)))
-        self._ctx_cache[key] = mixed
+        self._ctx_cache.pop(key, None)         # a same-address entry of a dead tensor, if any
+        self._ctx_cache[key] = (mixed, inputs)
         return mixed
+
+    def clear_context_cache(self):
+        """Drop the cached mixed contexts (and the condition tensors they keep alive)."""
+        self._ctx_cache.clear()
 
     @staticmethod
     def _condition_dropout(batch_size, context, ar_vision_input, classifier_free_ratio, unconditioned_context):

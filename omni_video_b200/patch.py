@@ -101,7 +101,7 @@ def patch_reference_unified(unified, sp_group=None):
     unified.context_cache_hits = 0
     unified.context_cache_misses = 0
     cls = U.UnifiedWanWithMixedConditionModel
-    for name in ("_vlm", "_params_key", "_per_sample", "mixed_context", "forward"):
+    for name in ("_vlm", "_params_key", "_per_sample", "mixed_context", "clear_context_cache", "forward"):
         setattr(unified, name, types.MethodType(getattr(cls, name), unified))
     unified._condition_dropout = cls._condition_dropout        # a staticmethod: no binding
     adapter = getattr(unified, "visual_context_adapter", None)

@@ -1,6 +1,6 @@
 """Pipeline trace of one attention CTA (debug build scripts/microbench/build/libovb_trace.so, compiled with
--DOVB_ATTN_TRACE): clock64() stamps of the MMA thread and of one softmax lane per Q tile for KV
-tiles 64..71, printed relative to the first stamp.
+-DOVB_ATTN_TRACE by scripts/build_trace_lib.sh): clock64() stamps of the MMA thread and of one softmax lane
+for KV tiles 64..71, printed relative to the first stamp.
 """
 import ctypes as C
 import os
@@ -35,13 +35,22 @@ for _ in range(2):
     rc = lib.ovb_attn_fwd(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0
 torch.cuda.synchronize()
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+for i in range(5):
+    evs[i].record()
+    lib.ovb_attn_fwd(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+evs[5].record()
+torch.cuda.synchronize()
+ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(5))[2]
+print(f"{os.environ.get('OVB_TRACE_LIB', 'libovb_trace.so')}: L={L} H={H}: {ms:.3f} ms, {4.0 * LQ * L * H * 128 / ms / 1e9:.0f} TF/s (trace build)")
 t = trace.cpu().view(8, 32)
 t0 = int(t[0, 0])
-names = {0: "MMA  issue QK0", 1: "MMA  QK0 issued", 2: "MMA  PV1(j-1) issued", 3: "MMA  QK1 issued",
-         4: "MMA  P0 part seen", 5: "MMA  PV0 issued", 6: "MMA  P1(j-1) part seen",
-         8: "SM0  S seen", 9: "SM0  chunk0 loaded", 10: "SM0  3/4 done", 11: "SM0  exps issued",
-         12: "SM0  P published", 16: "SM1  S seen", 17: "SM1  chunk0 loaded", 18: "SM1  3/4 done",
-         19: "SM1  exps issued", 20: "SM1  P published"}
+names = {0: "MMA  QK(j) issued", 1: "MMA  P(j) NOT ready after QK issue", 2: "MMA  P(j) ready, issuing PV", 3: "MMA  PV(j) issued", 4: "MMA  spin for P(j) done", 5: "MMA  fenced, P(j) usable"}
+for q in range(4):
+    names[16 + q] = f"SM{q}  S(j) seen"
+    names[20 + q] = f"SM{q}  max known"
+    names[24 + q] = f"SM{q}  decided"
+    names[28 + q] = f"SM{q}  P published"
 ev = []
 for j in range(8):
     for slot, nm in names.items():
@@ -52,9 +61,9 @@ prev = 0
 for ts, j, nm in ev:
     print(f"{ts:8d} (+{ts - prev:5d})  j={j}  {nm}")
     prev = ts
-per_step = (int(t[7, 0]) - int(t[0, 0])) / 7.0
-print(f"cycles per KV step: {per_step:.0f}")
+per_step = (int(t[7, 2]) - int(t[0, 2])) / 7.0
+print(f"cycles per KV tile (PV issue -> PV issue): {per_step:.0f}")
 for j in range(1, 7):
-    sm0 = int(t[j, 12]) - int(t[j, 8]); sm1 = int(t[j, 20]) - int(t[j, 16])
-    print(f"j={j+64}: softmax0 S-seen->P-published {sm0}, (load0 {int(t[j,9])-int(t[j,8])}, 3/4 {int(t[j,10])-int(t[j,9])}, "
-          f"rest {int(t[j,11])-int(t[j,10])}, publish {int(t[j,12])-int(t[j,11])}); softmax1 {sm1}")
+    for q in range(4):
+        print(f"j={j+64} quad {q}: S seen->max known {int(t[j,20+q])-int(t[j,16+q])}, ->decided {int(t[j,24+q])-int(t[j,20+q])}, "
+              f"->published {int(t[j,28+q])-int(t[j,24+q])}; published -> MMA issues PV {int(t[j,2])-int(t[j,28+q])}")

@@ -87,10 +87,10 @@ def bench_attn(L, H, Lk, res):
     r = dict(kind="attn", L=L, H=H, Lk=Lk, ovb_ms=med, ovb_tflops=fl / med / 1e9)
     line = f"attn L={L} Lk={Lk} H={H}: ovb {med:.3f} ms {r['ovb_tflops']:.0f} TF/s"
     items = ((L + 255) // 256) * H
-    if items % 148 and Lk >= 4096:
+    if items % 74 and Lk >= 4096:
         med_w, _ = time_fn(lambda: ops.attention(q, k, v, out=out, split_keys=False), iters=5, warmup=2)
         r.update(whole_items_ms=med_w, whole_items_tflops=fl / med_w / 1e9)
-        line += f" (one CTA per item: {med_w:.3f} ms {fl / med_w / 1e9:.0f} TF/s; {items} items on 148 SMs)"
+        line += f" (one CTA per item: {med_w:.3f} ms {fl / med_w / 1e9:.0f} TF/s; {items} items on 74 CTA pairs)"
     try:
         import flash_attn
         fa = lambda: flash_attn.flash_attn_func(q, k, v)  # noqa: E731
@@ -131,10 +131,12 @@ def main():
     shapes = [(L, 4608, 1536), (L, 1536, 1536), (L, 8960, 1536), (L, 1536, 8960)]
     if not quick:
         shapes += [(8192, 8192, 8192), (L, 15360, 5120), (L, 5120, 5120), (L, 13824, 5120), (L, 5120, 13824)]
-    for s in shapes:
-        bench_gemm(*s, res)
-    bench_gemm_resid(L, 1536, 1536, res)
-    bench_gemm_resid(L, 1536, 8960, res)
+    attn_only = "--attn-only" in sys.argv
+    if not attn_only:
+        for s in shapes:
+            bench_gemm(*s, res)
+        bench_gemm_resid(L, 1536, 1536, res)
+        bench_gemm_resid(L, 1536, 8960, res)
     bench_attn(4096, 12, 4096, res)
     bench_attn(L, 12, L, res)
     bench_attn(L, 12, 512, res)
@@ -142,7 +144,11 @@ def main():
     bench_attn(L, 6, L, res)    # cfg2 x ulysses2 on 4 GPUs: 768 items = 5.2 waves
     if not quick:
         bench_attn(L, 40, L, res)
-    bench_elementwise(L, 1536, res)
+    if not attn_only:
+        bench_elementwise(L, 1536, res)
+    else:
+        bench_attn(L, 12, 6144, res)
+        bench_attn(75600, 5, 75600, res)   # A14B 720p per-rank shape on 8 GPUs
     if "--json" in sys.argv:
         path = sys.argv[sys.argv.index("--json") + 1]
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)

@@ -43,6 +43,34 @@ def test_mixed_context_host_logic_matches_reference_golden(name):
     assert again[0] is outs[0] and (m.context_cache_hits, m.context_cache_misses) == (1, 1)
 
 
+def test_context_cache_is_not_fooled_by_recycled_addresses():
+    """Two successive prompts of equal length: the second must get ITS context even when its tensors
+    land on the addresses the first prompt's (freed) tensors had.  The cache entry keeps its inputs alive
+    (so a live entry's key cannot collide) and confirms every hit by object identity."""
+    meta, _ = load_golden("unified_batch2_noadapter")
+    cfg, sd, ar, ctx, vis, st = unified_case(meta)
+    m = build_cpu(meta, cfg, sd)
+    n = len(meta["n_text"])
+    dev = torch.device("cpu")
+    ctx_a = [c.clone() for c in ctx]
+    out_a = [o.clone() for o in m.mixed_context(n, ctx_a, ar, vis, st, device=dev)]
+    held = next(iter(m._ctx_cache.values()))[1]
+    assert any(t is ctx_a[0] for t in held)             # the entry pins its inputs
+    # forge the collision the allocator would produce: an entry under prompt B's key that was computed
+    # from other (dead) tensors
+    ctx_b = [c.clone() + 1.0 for c in ctx]
+    from omni_video_b200.modules import unified_model as UM
+    key_b = (n, UM._ident(ctx_b), UM._ident(ar), UM._ident(vis), UM._ident(st), m._params_key(), m.max_context_len)
+    m._ctx_cache[key_b] = (out_a, [torch.empty(0)] * len(held))
+    out_b = m.mixed_context(n, ctx_b, ar, vis, st, device=dev)
+    assert out_b is not out_a
+    assert not all(torch.equal(a, b) for a, b in zip(out_a, out_b))
+    ref_b = [o.clone() for o in out_b]
+    m.clear_context_cache()
+    again = m.mixed_context(n, ctx_b, ar, vis, st, device=dev)
+    assert all(torch.equal(a, b) for a, b in zip(ref_b, again))
+
+
 def test_forward_dropout_rng_and_errors_on_cpu():
     meta, _ = load_golden("unified_batch2_noadapter")
     cfg, sd, ar, ctx, vis, st = unified_case(meta)
