@@ -254,8 +254,11 @@ def run_ours(args):
     init_random_(model, 1818)
     if sp_group is not None and sp > 1:
         model.sp_group = sp_group
-    use_graph = bool(args.graph)  # opt-in: see --graph
-    model.use_cuda_graph = use_graph
+    # CUDA-graph replay of the forward: default whenever sequence parallelism cuts the kernels short
+    # (N >= 4 here); the captured graph holds this library's kernels only (no NCCL op: the final
+    # gather runs eagerly after every replay), see --graph / --no-graph
+    use_graph = bool(args.graph) if args.graph is not None else (sp > 1)
+    model.use_cuda_graph = False
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1818)
@@ -276,6 +279,46 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---------------- parity of the parallel layout, before anything is timed ----------------
+    # The same forward (conditional branch, step-0 inputs) on the sequence-parallel layout, with the
+    # peer-memory transport and with the NCCL all-to-all transport, against the SINGLE-GPU forward of
+    # the same inputs (every rank holds the full weights; reference semantics:
+    # distributed/full_sequence_parallel.py:123-126,163 and ulysses.py:41-55 are re-orderings of the
+    # single-GPU computation).
+    parity = None
+    if world > 1:
+        t_par = torch.full((1,), 999, device=dev, dtype=torch.int64)
+        if sp > 1:
+            from omni_video_b200.distributed import peer as peer_mod
+            o_sp = model([latent0], t=t_par, context=[ctx_c], seq_len=seq_len)[0].clone()
+            tr = next((v for v in peer_mod._transports.values() if v), None)
+            if tr is not None:
+                tr.check()
+            prev = os.environ.get("OVB_SP_TRANSPORT")
+            os.environ["OVB_SP_TRANSPORT"] = "nccl"
+            o_nccl = model([latent0], t=t_par, context=[ctx_c], seq_len=seq_len)[0].clone()
+            if prev is None:
+                os.environ.pop("OVB_SP_TRANSPORT")
+            else:
+                os.environ["OVB_SP_TRANSPORT"] = prev
+            model.sp_group = None
+            o_one = model([latent0], t=t_par, context=[ctx_c], seq_len=seq_len)[0]
+            model.sp_group = sp_group
+            err = float((o_sp.double() - o_one.double()).norm() / o_one.double().norm())
+            stats = torch.tensor([err, 0.0 if torch.equal(o_sp, o_nccl) else 1.0,
+                                  0.0 if bool(torch.isfinite(o_sp).all()) else 1.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+            parity = dict(sp_vs_single_rel_l2=float(f"{stats[0].item():.3e}"),
+                          peer_vs_nccl_equal=bool(stats[1].item() == 0.0), finite=bool(stats[2].item() == 0.0),
+                          transport=(tr.backend if tr is not None else "nccl"),
+                          what=f"one forward, {L} tokens, ulysses{sp} vs the same forward on one GPU, max over ranks")
+            del o_sp, o_nccl, o_one
+        else:
+            parity = dict(sp_vs_single_rel_l2=0.0, peer_vs_nccl_equal=None, finite=True, transport=None,
+                          what="cfg2 only: every forward runs whole on one GPU (nothing is sharded)")
+        torch.cuda.empty_cache()
+    model.use_cuda_graph = use_graph
 
     # ---------------- device-resident run (value) ----------------
     latent = latent0.clone()
@@ -346,20 +389,30 @@ def run_ours(args):
         vae = vae_decode_leg((Fr, H, W), dev, peaks, dist.group.WORLD if world > 1 else None, world)
 
     def shutdown():
-        """Leave the job.  A live CUDA graph that holds a captured NCCL collective (the sequence-parallel
-        forward's final all-gather) makes destroy_process_group() wait for ever, so in graph mode the
-        graphs are dropped first and the process leaves without tearing NCCL down."""
+        """Leave the job: drop the captured graphs, then tear NCCL down.  (Round 1 captured the final
+        all-gather inside the graph and destroy_process_group() then waited for ever; the capture now
+        ends before the gather.  A watchdog still guarantees that a teardown problem cannot hang the
+        job after the result line has been printed.)"""
         if world == 1:
             return
         torch.cuda.synchronize()
-        if use_graph:
-            dist.barrier()                      # leave together: rank 0 prints its line before anyone goes
-            torch.cuda.synchronize()
+        dist.barrier()                          # leave together: rank 0 prints its line before anyone goes
+        torch.cuda.synchronize()
+        if use_graph and getattr(model, "_engine", None) is not None:
             model._engine._graphs.clear()
-            sys.stdout.flush()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        import threading
+
+        def _bail():
+            sys.stderr.write(f"[rank {rank}] destroy_process_group did not return within 30 s; leaving\n")
             sys.stderr.flush()
             os._exit(0)
+        timer = threading.Timer(30.0, _bail)
+        timer.daemon = True
+        timer.start()
         dist.destroy_process_group()
+        timer.cancel()
 
     if rank != 0:
         shutdown()
@@ -380,15 +433,18 @@ def run_ours(args):
     try:  # per-launch DRAM bytes of the self-attention launch from the committed ncu capture
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             tj = json.load(fh)["attn_fwd_kernel"]
-        key = f"B1_H{heads // sp}_Lq{seq_len}_Lk{seq_len}"
+        b_timed = 2 if stepper.batch_cfg else 1
+        key = f"B{b_timed}_H{heads // sp}_Lq{seq_len}_Lk{seq_len}"
         traffic = tj.get(key)
     except Exception:
         traffic = None
     roofline = dict(bound="tensor", kernel="attn_fwd_kernel (self+cross flash attention, tcgen05)",
                     achieved=round(attn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
                     frac=round(attn_tf / peaks["tflops"], 4), traffic=traffic,
-                    traffic_note="DRAM bytes of one self-attention launch (ncu --set full, profiles/); "
-                                 "algorithmic q+k+v+o bytes are the same 402.6 MB",
+                    traffic_note=(f"DRAM bytes of one self-attention launch of the timed shape "
+                                  f"(B={2 if stepper.batch_cfg else 1}, {heads // sp} heads, {seq_len} tokens; "
+                                  "ncu --set full, profiles/ncu_traffic.json); algorithmic q+k+v+o bytes = "
+                                  f"{(2 if stepper.batch_cfg else 1) * 4 * seq_len * (heads // sp) * 128 * 2 / 1e6:.1f} MB"),
                     peak_source=peaks["source"],
                     launches=agg.get("attn", [0, 0, 0])[2],
                     ms_per_launch=round(agg["attn"][1] / max(1, agg["attn"][2]), 4) if "attn" in agg else None,
@@ -421,6 +477,8 @@ def run_ours(args):
                 e2e=dict(value=round(args.steps / (e2e_ms / 1e3), 5), unit="steps/s",
                          h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=int(launches), clocks=clk, roofline=roofline)
+    if parity is not None:
+        line["parity"] = parity
     if vae is not None:
         line["vae_decode"] = vae
     if cpu is not None:
@@ -468,6 +526,18 @@ def vae_decode_leg(grid_lat, dev, peaks, group=None, world=1):
             ms_it = float(tt.item())
         times.append(ms_it)
     tl, ops.timeline = ops.timeline, None
+    strips_vs_single = None
+    if group is not None:
+        # parity of the strip layout: the same decode whole on this GPU (bf16 kernels in a different
+        # tiling order: equal up to accumulation-order rounding)
+        vae.set_strip_group(None)
+        whole = vae.decode([z])[0]
+        d = (out - whole).abs().max()
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        mse = float(((out.double() - whole.double()) ** 2).mean().item())
+        strips_vs_single = dict(max_abs=float(f"{d.item():.3e}"),
+                                psnr_db=round(10.0 * math.log10(4.0 / max(mse, 1e-30)), 1))
+        del whole
     conv_fl = sum(t[1] for t in tl if t[0] == "conv")
     conv_ms = sum(t[3].elapsed_time(t[4]) for t in tl if t[0] == "conv")
     norm_b = sum(t[1] for t in tl if t[0] == "norm")
@@ -481,6 +551,8 @@ def vae_decode_leg(grid_lat, dev, peaks, group=None, world=1):
                norm_kernel=dict(gbs=round(norm_b / max(norm_ms, 1e-9) / 1e6, 1), share=round(norm_ms / ms, 3),
                                 frac_of_hbm_peak=round(norm_b / max(norm_ms, 1e-9) / 1e6 / peaks["hbm"], 4)),
                finite=bool(torch.isfinite(out).all().item()))
+    if strips_vs_single is not None:
+        res["parity_strips_vs_single_gpu"] = strips_vs_single
     del out, vae
     torch.cuda.empty_cache()
     return res
@@ -563,7 +635,8 @@ def run_reference(args):
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=f"OmniVideo2-{args.model} DiT, {args.video} (latent 16x{Fr}x{H}x{W}, "
                                      f"{L} tokens), text_len {args.text_len}, reference CPU path "
-                                     "(PyTorch fp32 restatement, host cores)"),
+                                     "(PyTorch fp32 restatement, host cores), EXTRAPOLATED from a bounded "
+                                     "sample: see cpu_baseline.sample", extrapolated=True),
                 e2e=dict(value=last["value"], unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, cpu_baseline=last)
     print(json.dumps(line), flush=True)
@@ -590,9 +663,8 @@ def main():
                          "the head count would allow one group of N (what N=8 does for 12 heads)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--graph", dest="graph", action="store_true", default=None,
-                    help="replay the DiT forward as a CUDA graph (opt-in: +1 %% at 2 GPUs, 7.74 vs 6.9 steps/s at 4; "
-                         "off by default because job teardown with NCCL collectives captured in a live graph "
-                         "is only handled by leaving without destroy_process_group)")
+                    help="replay the DiT forward as a CUDA graph; default: on when the forward is "
+                         "sequence-parallel (kernels a fraction of a millisecond long), off otherwise")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":

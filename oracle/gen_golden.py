@@ -1,6 +1,8 @@
 """ORACLE support — generates tests/golden/*.npz by running the UNMODIFIED reference
 (/root/reference, imported by oracle/ref_loader.py) on the synthetic weights/inputs of
 oracle/synth.py.  Run in the build container:   python -m oracle.gen_golden
+(`python -m oracle.gen_golden --full` writes only the three big fixtures: full-depth 1.3B at BASELINE
+config 1, the A14B width at 2 layers, and the VAE decode of config 1's latent.)
 
 Each fixture stores only the recipe (config, seeds, shapes) and the reference's OUTPUT, so that
 tests regenerate identical weights/inputs from the seeds and compare (a) the oracle restatement in
@@ -95,10 +97,70 @@ def run_ragged_case(ref):
     print(f"wrote {path}: shapes {[tuple(o.shape) for o in out]}")
 
 
+# BASELINE.json configs[0] exactly: OmniVideo2-1.3B (30 layers, dim 1536, 12 heads), one forward on a
+# 17x256x256 video = latent [16, 5, 32, 32] = 1280 tokens, T5 context [77, 4096], fp32 on CPU
+# (reference model.py:417-524 end to end at FULL DEPTH: this is where bf16 error accumulates).
+FULL_1_3B = dict(name="dit_1_3B_config1", grid=(5, 32, 32), ctx_len=77, t=999)
+
+
+def run_full_1_3b(ref):
+    case = FULL_1_3B
+    cfg = dict(synth.DIT_1_3B)
+    model = ref.model.WanModel(**cfg)
+    model.load_state_dict(synth.dit_state_dict(cfg, seed=1818), strict=True)
+    model.eval().requires_grad_(False)
+    xs, t, ctx = synth.dit_inputs(cfg, case["grid"], case["ctx_len"], seed=7, batch=1, timestep=case["t"])
+    Fr, H, W = case["grid"]
+    seq_len = Fr * (H // 2) * (W // 2)
+    with torch.no_grad():
+        out = model(xs, t=t, context=ctx, seq_len=seq_len)
+    meta = dict(kind="dit_forward_full", cfg=cfg, grid=case["grid"], ctx_len=case["ctx_len"], seq_len=seq_len,
+                batch=1, t=case["t"], weight_seed=1818, input_seed=7,
+                reference="omnivideo/modules/model.py WanModel.forward, OmniVideo2-1.3B config "
+                          "(configs/wan_t2v_1_3B.py), BASELINE.json configs[0], fp32 CPU")
+    path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+    np.savez_compressed(path, meta=json.dumps(meta), out0=out[0].numpy())
+    print(f"wrote {path}: out0 shape {tuple(out[0].shape)} absmax {out[0].abs().max():.4f} "
+          f"rms {out[0].pow(2).mean().sqrt():.4f}")
+
+
+# OmniVideo2-A14B WIDTH (dim 5120, 40 heads, ffn 13824: configs/wan_t2v_A14B.py) at 2 layers and
+# 2160 tokens (latent [16, 5, 36, 48]): the GEMM shapes (5120 x 15360 / 5120 / 13824) and the 40-head
+# attention of BASELINE.json configs[2-3], at a depth the CPU reference finishes in a minute.
+WIDE_A14B = dict(name="dit_A14B_width_2layers", grid=(5, 36, 48), ctx_len=40, t=400, num_layers=2, text_len=64)
+
+
+def run_wide_a14b(ref):
+    case = WIDE_A14B
+    cfg = dict(synth.DIT_A14B, num_layers=case["num_layers"], text_len=case["text_len"])
+    model = ref.model.WanModel(**cfg)
+    model.load_state_dict(synth.dit_state_dict(cfg, seed=1818), strict=True)
+    model.eval().requires_grad_(False)
+    xs, t, ctx = synth.dit_inputs(cfg, case["grid"], case["ctx_len"], seed=7, batch=1, timestep=case["t"])
+    Fr, H, W = case["grid"]
+    seq_len = Fr * (H // 2) * (W // 2)
+    with torch.no_grad():
+        out = model(xs, t=t, context=ctx, seq_len=seq_len)
+    meta = dict(kind="dit_forward_full", cfg=cfg, grid=case["grid"], ctx_len=case["ctx_len"], seq_len=seq_len,
+                batch=1, t=case["t"], weight_seed=1818, input_seed=7,
+                reference="omnivideo/modules/model.py WanModel.forward at the OmniVideo2-A14B width "
+                          "(configs/wan_t2v_A14B.py: dim 5120, 40 heads, ffn 13824), 2 layers, fp32 CPU")
+    path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+    np.savez_compressed(path, meta=json.dumps(meta), out0=out[0].numpy())
+    print(f"wrote {path}: out0 shape {tuple(out[0].shape)} absmax {out[0].abs().max():.4f} "
+          f"rms {out[0].pow(2).mean().sqrt():.4f}")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = ref_loader.load_reference(cpu_attention=True)
+    if "--full" in sys.argv:                 # ~6 GB of fp32 weights, ~1 minute: on request only
+        run_full_1_3b(ref)
+        run_wide_a14b(ref)
+        from oracle import gen_golden_vae
+        gen_golden_vae.main_big(ref)
+        return
     run_i2v_case(ref)
     run_ragged_case(ref)
     for case in DIT_CASES:

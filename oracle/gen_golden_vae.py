@@ -23,6 +23,31 @@ CASES = [
 ]
 
 
+# BASELINE.json configs[0]'s video: latent [16, 5, 32, 32] -> [3, 17, 256, 256].  The fixture keeps every
+# 4th pixel in H and W (all frames, all channels): 0.8 MB instead of 13; PSNR over the kept positions.
+BIG_CASE = dict(name="vae_dec_config1", kind="vae_decode_strided", grid=(5, 32, 32), stride=4)
+
+
+def main_big(ref):
+    sd = synth.vae_state_dict(seed=1818)
+    model = ref.vae.WanVAE_(**VAE_CFG)
+    model.load_state_dict(sd, strict=True)
+    model.eval().requires_grad_(False)
+    scale = [torch.tensor(LATENT_MEAN), 1.0 / torch.tensor(LATENT_STD)]
+    case = BIG_CASE
+    with torch.no_grad():
+        z = synth.vae_latent(case["grid"], seed=7)
+        out = model.decode(z.unsqueeze(0), scale).float().clamp_(-1, 1).squeeze(0)
+    st = case["stride"]
+    kept = out[:, :, ::st, ::st].contiguous()
+    meta = dict(case, weight_seed=1818, input_seed=7, full_shape=list(out.shape),
+                reference="omnivideo/modules/vae2_1.py WanVAE_.decode (chunked, feat_cache), fp32 CPU; "
+                          "out0 = decoded[:, :, ::4, ::4]")
+    path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+    np.savez_compressed(path, meta=json.dumps(meta), out0=kept.numpy())
+    print(f"wrote {path}: full {tuple(out.shape)} kept {tuple(kept.shape)} absmax {out.abs().max():.4f} std {out.std():.4f}")
+
+
 def main(ref):
     sd = synth.vae_state_dict(seed=1818)
     model = ref.vae.WanVAE_(**VAE_CFG)

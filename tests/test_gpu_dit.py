@@ -54,6 +54,31 @@ def test_dit_forward_vs_bf16_oracle(name):
         assert err <= 5e-3, f"{name}: rel-L2 vs bf16 oracle {err}"
 
 
+@pytest.mark.parametrize("name", golden_names("dit_forward_full"))
+def test_dit_at_baseline_configs_vs_reference_golden(name):
+    """dit_1_3B_config1: the FULL-DEPTH OmniVideo2-1.3B (30 layers, dim 1536, 12 heads) at
+    BASELINE.json configs[0] (latent [16, 5, 32, 32] = 1280 tokens, context [77, 4096]);
+    dit_A14B_width_2layers: dim 5120 / 40 heads / ffn 13824 (the A14B GEMM shapes and head count) at
+    2 layers, 2160 tokens.  North-star tolerance: per-step latent rel-L2 <= 1e-2 against what the
+    reference itself computed in fp32; and against the bf16-emulating oracle on bf16-rounded inputs."""
+    meta, gold = load_golden(name)
+    cfg, sd, xs, t, ctx, seq_len = dit_case(meta)
+    model = _build(cfg, sd)
+    out = model([x.cuda() for x in xs], t=t.cuda(), context=[c.cuda() for c in ctx], seq_len=seq_len)[0]
+    torch.cuda.synchronize()
+    assert out.shape == gold[0].shape and torch.isfinite(out).all()
+    e_gold = O.rel_l2(out.cpu(), gold[0])
+    xs_b, ctx_b = [x.to(bf16) for x in xs], [c.to(bf16) for c in ctx]
+    out_b = model([x.cuda() for x in xs_b], t=t.cuda(), context=[c.cuda() for c in ctx_b], seq_len=seq_len)[0]
+    ref = O.dit_forward(synth.round_bf16(sd), cfg, [x.float() for x in xs_b], t,
+                        [c.float() for c in ctx_b], seq_len, emulate_bf16=True)[0]
+    e_emu = O.rel_l2(out_b.cpu(), ref)
+    print(f"{name}: {cfg['num_layers']} layers, dim {cfg['dim']}, {seq_len} tokens: rel-L2 vs reference fp32 "
+          f"{e_gold:.3e}, vs bf16 oracle {e_emu:.3e} (oracle bf16 vs reference {O.rel_l2(ref, gold[0]):.3e})")
+    assert e_gold <= 1e-2, f"{name}: rel-L2 vs reference {e_gold}"
+    assert e_emu <= 8e-3, f"{name}: rel-L2 vs bf16 oracle {e_emu}"
+
+
 def test_dit_medium_vs_bf16_oracle():
     """4 heads, 3 layers, 2340 tokens (not a multiple of the 128/256 tile sizes), padded seq_len."""
     cfg = dict(synth.TINY_DIT, dim=512, num_heads=4, ffn_dim=1024, num_layers=3, text_len=64)

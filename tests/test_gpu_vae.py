@@ -208,6 +208,22 @@ def test_decode_vs_reference_golden(name):
     assert p_emu >= 45.0
 
 
+def test_decode_at_baseline_config1_vs_reference_golden():
+    """latent [16, 5, 32, 32] -> video [3, 17, 256, 256] (BASELINE.json configs[0]) against every 4th
+    pixel of the reference's own decode, and the whole frame against the fp32 oracle."""
+    meta, gold = _load("vae_dec_config1")
+    sd = synth.vae_state_dict(seed=meta["weight_seed"])
+    z = synth.vae_latent(tuple(meta["grid"]), seed=meta["input_seed"])
+    out = _vae(sd).decode([z.cuda()])[0].cpu()
+    assert list(out.shape) == meta["full_shape"] and float(out.abs().max()) <= 1.0
+    st = meta["stride"]
+    p_ref = V.psnr(out[:, :, ::st, ::st], gold)
+    full = V.vae_decode(sd, z)
+    p_full = V.psnr(out, full)
+    print(f"vae_dec_config1: PSNR vs reference fp32 (strided) {p_ref:.1f} dB, vs fp32 oracle (all pixels) {p_full:.1f} dB")
+    assert p_ref >= 40.0 and p_full >= 40.0, "north-star tolerance: decoded-video PSNR >= 40 dB"
+
+
 @pytest.mark.parametrize("name", golden_names("vae_encode"))
 def test_encode_vs_reference_golden(name):
     meta, gold = _load(name)

@@ -49,3 +49,17 @@ def test_bf16_emulation_meets_psnr_target():
     z = synth.vae_latent(tuple(meta["grid"]), seed=meta["input_seed"])
     out = V.vae_decode(sd, z, emulate_bf16=True)
     assert V.psnr(out, gold) >= 40.0
+
+
+def test_decode_at_baseline_config1_matches_reference():
+    """latent [16, 5, 32, 32] -> [3, 17, 256, 256] (BASELINE.json configs[0]); the fixture keeps every
+    4th pixel of the reference's output."""
+    meta, gold = _load("vae_dec_config1")
+    sd = synth.vae_state_dict(seed=meta["weight_seed"])
+    z = synth.vae_latent(tuple(meta["grid"]), seed=meta["input_seed"])
+    out = V.vae_decode(sd, z)
+    assert list(out.shape) == meta["full_shape"]
+    st = meta["stride"]
+    kept = out[:, :, ::st, ::st]
+    assert (kept - gold).abs().max().item() <= 5e-4
+    assert V.psnr(kept, gold) > 80.0
