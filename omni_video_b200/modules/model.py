@@ -302,13 +302,17 @@ class DiTEngine:
         # ---- time embedding (fp32 math on bf16-stored weights, :466-476), one row per sample
         t = t.to(dev)
         if t.dim() == 2:
-            if not bool((t == t[:, :1]).all()):
-                raise NotImplementedError(
-                    "per-token timesteps (t of shape [B, L] with different values inside a sample) "
-                    "are not implemented on the B200 path yet; Omni-Video's pipeline passes t [B]")
-            t = t[:, 0]
-        assert t.numel() == B
-        sin = ops.sinusoidal_embedding(t.reshape(-1), m.freq_dim)                   # [B, 256]
+            # per-token timesteps t [B, seq_len] (reference model.py:466-476 embeds every token's own
+            # t).  Uniform inside every sample -> the one-row-per-sample fast path (identical
+            # numerics); otherwise one embedding row per token of this rank: e [B*s_loc, d],
+            # e0 [B*s_loc, 6d], and the blocks read their modulation per ROW.
+            assert t.shape == (B, seq_len), f"t must be [B] or [B, seq_len]; got {tuple(t.shape)}"
+            if bool((t == t[:, :1]).all()):
+                t = t[:, 0]
+            else:
+                t = t[:, row0:row0 + s_loc].contiguous()
+        assert t.numel() in (B, B * s_loc)
+        sin = ops.sinusoidal_embedding(t.reshape(-1), m.freq_dim)                   # [B | B*s_loc, 256]
         e = ops.linear_f32(ops.linear_f32(sin, P.time_w0, P.time_b0, act_out=1),
                            P.time_w2, P.time_b2)                                    # [B, d]
         e0 = ops.linear_f32(e, P.tproj_w, P.tproj_b, act_in=1)                      # [B, 6d]
@@ -381,8 +385,11 @@ class DiTEngine:
         row0 = rank * s_loc
         M = B * s_loc
         Lc = m.text_len
-        mod = ops.modulation_table(P.block_mod, e0, True)       # [N, B, 6, d] fp32
-        hmod = ops.modulation_table(P.head_mod, e, False)       # [1, B, 2, d] fp32
+        per_token = e.shape[0] != B                             # t was [B, seq_len] with distinct values
+        # modulation = block parameter + time embedding: one row per sample [N, B, 6, d] fp32, or — with
+        # per-token timesteps — one row per token, built layer by layer ([M, 6, d] is 1.2 GB at 32760 tokens)
+        mod = None if per_token else ops.modulation_table(P.block_mod, e0, True)
+        hmod = ops.modulation_table(P.head_mod, e, False)       # [1, B | M, 2, d] fp32
 
         # ---- work buffers
         hbuf = torch.empty((M, d), device=dev, dtype=bf16)
@@ -410,7 +417,8 @@ class DiTEngine:
         #                                                 sample to seq_len) rotates each sample with its own grid
 
         for li, W in enumerate(P.blocks):
-            mb = mod[li]  # [B, 6, d]: shift_sa, scale_sa, gate_sa, shift_ffn, scale_ffn, gate_ffn
+            # [B | M, 6, d]: shift_sa, scale_sa, gate_sa, shift_ffn, scale_ffn, gate_ffn
+            mb = ops.modulation_table(P.block_mod[li:li + 1], e0, True)[0] if per_token else mod[li]
             # ---------------- self attention
             ops.layernorm_modulate(xres, mb[:, 1], mb[:, 0], eps, rows_per_sample=s_loc,
                                    round_ln_bf16=(li == 0), out=hbuf)

@@ -206,11 +206,13 @@ def dit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: List[torch.Tensor], t
         emb = linear(tok, sd["patch_embedding.weight"].flatten(1), sd["patch_embedding.bias"], em)
         xs = torch.cat([emb, emb.new_zeros(seq_len - L, d)])                      # :461-464
         # time :466-476 (fp32 math on the stored weights)
-        tb = t[b].reshape(1)
+        per_token = t.dim() == 2                       # t [B, seq_len]: every token its own timestep (:466-467)
+        tb = t[b].reshape(-1) if per_token else t[b].reshape(1)
         sin = sinusoidal_embedding_1d(cfg["freq_dim"], tb).float()
         e = F.linear(F.silu(F.linear(sin, sd["time_embedding.0.weight"], sd["time_embedding.0.bias"])),
-                     sd["time_embedding.2.weight"], sd["time_embedding.2.bias"])   # [1, d]
-        e0 = F.linear(F.silu(e), sd["time_projection.1.weight"], sd["time_projection.1.bias"]).view(6, d)
+                     sd["time_embedding.2.weight"], sd["time_embedding.2.bias"])   # [1 | seq_len, d]
+        e0 = F.linear(F.silu(e), sd["time_projection.1.weight"], sd["time_projection.1.bias"])
+        e0 = e0.view(-1, 6, d) if per_token else e0.view(6, d)
         # context :478-485
         c = context[b].float()
         c = torch.cat([c, c.new_zeros(cfg["text_len"] - c.shape[0], c.shape[1])])
@@ -220,8 +222,8 @@ def dit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: List[torch.Tensor], t
         for li in range(nl):
             xs = block_forward(sd, f"blocks.{li}.", xs, e0, L, grid, angles, c, H, eps, em, li == 0)
         # head :278-290 (fp32)
-        hm = sd["head.modulation"].reshape(2, d) + e                               # shift, scale
-        hn = layer_norm(xs, eps) * (1 + hm[1]) + hm[0]
+        hm = sd["head.modulation"].reshape(2, d) + e.unsqueeze(-2)                 # [1 | seq_len, 2, d]: shift, scale
+        hn = layer_norm(xs, eps) * (1 + hm[:, 1]) + hm[:, 0]
         y = F.linear(hn, sd["head.head.weight"], sd["head.head.bias"])
         outs.append(unpatchify(y, grid, cfg["out_dim"]).float())
     return outs

@@ -151,6 +151,26 @@ def run_wide_a14b(ref):
           f"rms {out[0].pow(2).mean().sqrt():.4f}")
 
 
+def run_pertoken_case(ref):
+    """t of shape [B, seq_len] with a different timestep per token (model.py:466-476): every token gets
+    its own time embedding and modulation row."""
+    cfg = dict(synth.TINY_DIT)
+    model = ref.model.WanModel(**cfg)
+    model.load_state_dict(synth.dit_state_dict(cfg, seed=1818), strict=True)
+    model.eval().requires_grad_(False)
+    grid, seq_len = (2, 6, 8), 28                                   # 24 tokens + 4 padded rows
+    xs, _, ctx = synth.dit_inputs(cfg, grid, 9, seed=7, batch=2, timestep=0)
+    t = torch.stack([(torch.arange(seq_len) * 37 + 11 + 400 * b) % 1000 for b in range(2)]).to(torch.int64)
+    with torch.no_grad():
+        out = model(xs, t=t, context=ctx, seq_len=seq_len)
+    meta = dict(kind="dit_forward_pertoken", cfg=cfg, grid=grid, ctx_len=9, seq_len=seq_len, batch=2,
+                t_rule="(arange(seq_len) * 37 + 11 + 400 * b) % 1000", weight_seed=1818, input_seed=7,
+                reference="omnivideo/modules/model.py WanModel.forward with t [B, seq_len], fp32 CPU")
+    path = os.path.join(GOLDEN_DIR, "dit_tiny_pertoken.npz")
+    np.savez_compressed(path, meta=json.dumps(meta), out0=out[0].numpy(), out1=out[1].numpy())
+    print(f"wrote {path}: shapes {[tuple(o.shape) for o in out]}")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -163,6 +183,7 @@ def main():
         return
     run_i2v_case(ref)
     run_ragged_case(ref)
+    run_pertoken_case(ref)
     for case in DIT_CASES:
         cfg, seq_len, outs = run_dit_case(ref, case)
         meta = dict(kind="dit_forward", cfg=cfg, grid=case["grid"], ctx_len=case["ctx_len"],

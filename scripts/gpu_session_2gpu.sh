@@ -1,7 +1,11 @@
-cd /root/repo
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/sp_check.py 2>&1 | grep rank
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 3 --no-vae 2>gpurun_out/bench2.err | tee gpurun_out/bench_2gpu.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 2 --warmup 3 --cfg-split --no-vae 2>gpurun_out/bench2c.err | tee gpurun_out/bench_2gpu_cfgsplit.json
-tail -3 gpurun_out/bench2.err gpurun_out/bench2c.err
-CUDA_VISIBLE_DEVICES=0 python bench.py --model A14B --steps 1 --warmup 1 --no-cpu-baseline 2>gpurun_out/bench_a14b.err | tee gpurun_out/bench_a14b_480p.json
-tail -3 gpurun_out/bench_a14b.err
+#!/bin/bash
+# 2-GPU session: parity of the parallel layouts on hardware (logs kept for profiles/), then bench lines.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
+run 29511 scripts/sp_check.py 2>&1 | grep -E "rank|Error|error" | tee gpurun_out/sp_check_2gpu.log
+run 29512 scripts/vae_strip_check.py 2>&1 | grep -E "rank|Error|error" | tee gpurun_out/vae_strip_check_2gpu.log
+timeout 300 python -m pytest tests/test_gpu_dit.py tests/test_gpu_vae.py -m gpu -q -k "two_gpus" 2>&1 | tail -3 | tee gpurun_out/pytest_2gpu.log
+run 29513 bench.py --gpus 2 --steps 5 --warmup 3 2>gpurun_out/bench_2gpu.err | tee gpurun_out/bench_2gpu_cfg2.json
+run 29514 bench.py --gpus 2 --steps 5 --warmup 3 --no-cfg-split --no-vae 2>gpurun_out/bench_2gpu_u2.err | tee gpurun_out/bench_2gpu_ulysses2.json
+tail -3 gpurun_out/bench_2gpu.err gpurun_out/bench_2gpu_u2.err

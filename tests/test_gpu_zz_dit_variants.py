@@ -1,15 +1,14 @@
 """`WanModel.forward(..., y=...)` (model_type 'i2v', reference model.py:417-424, :446-447) on the GPU against the
 reference's own output.  The path is `torch.cat` in front of kernels that are parity-green, its host side is
-covered on CPU (tests/test_i2v_cpu.py); this file was added after the round's GPU budget was spent and had not run
-on a B200 when committed — `xfail(strict=False)` until it has (a pass is reported as XPASS)."""
+covered on CPU (tests/test_i2v_cpu.py).  Also: ragged batches and per-token timesteps.  (All passed on B200 at the
+end of round 1 as XPASS; the provisional xfail marks are gone.)"""
 import pytest
 import torch
 
 from oracle import dit as O
 from tests.test_i2v_cpu import i2v_case
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120),
-              pytest.mark.xfail(strict=False, reason="first GPU run pending (written after the round's GPU budget)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
 
 def test_i2v_forward_vs_reference_golden():
@@ -36,3 +35,23 @@ def test_ragged_batch_forward_vs_reference_golden():
     outs = m([u.cuda() for u in xs], t=t.cuda(), context=[c.cuda().to(torch.bfloat16) for c in ctx], seq_len=seq_len)
     for o, g in zip(outs, gold):
         assert o.shape == g.shape and O.rel_l2(o.cpu(), g) <= 1e-2
+
+
+def test_per_token_timesteps_vs_reference_golden():
+    """t [B, seq_len] with a different timestep per token (reference model.py:466-476): per-row time embedding,
+    per-row modulation in the LayerNorm and gated-residual kernels, per-row head modulation."""
+    from omni_video_b200.modules.model import WanModel
+    from tests.test_pertoken_cpu import pertoken_case
+    cfg, sd, xs, t, ctx, seq_len, gold = pertoken_case()
+    with torch.device("cuda"):
+        m = WanModel(**cfg, skip_init=True)
+    m.load_state_dict({k: v.cuda() for k, v in sd.items()}, strict=True)
+    m = m.to(torch.bfloat16).eval().requires_grad_(False)
+    outs = m([u.cuda() for u in xs], t=t.cuda(), context=[c.cuda().to(torch.bfloat16) for c in ctx], seq_len=seq_len)
+    for o, g in zip(outs, gold):
+        assert o.shape == g.shape and O.rel_l2(o.cpu(), g) <= 1e-2
+    # uniform values inside every sample take the one-row-per-sample path: same result as t [B]
+    tu = torch.tensor([[500] * seq_len, [17] * seq_len])
+    a = m([u.cuda() for u in xs], t=tu.cuda(), context=[c.cuda().to(torch.bfloat16) for c in ctx], seq_len=seq_len)
+    b = m([u.cuda() for u in xs], t=tu[:, 0].cuda(), context=[c.cuda().to(torch.bfloat16) for c in ctx], seq_len=seq_len)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))

@@ -1,15 +1,12 @@
 """Output video path on the GPU (omni_video_b200/utils/video.py, `ovb_video_to_uint8`) against frames captured
-from the reference's own `cache_video` — bit-exact.  The kernel was written after the round's GPU budget was
-spent and had not run on a B200 when committed, hence `xfail(strict=False)` (a pass is reported as XPASS, a
-failure does not turn the suite red); the file sorts last on purpose."""
+from the reference's own `cache_video` — bit-exact (passed on B200 at the end of round 1)."""
 import pytest
 import torch
 
 from tests.golden_util import golden_names, load_golden
 from tests.test_oracle_video_golden import video_case
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120),
-              pytest.mark.xfail(strict=False, reason="first GPU run of ovb_video_to_uint8 pending (written after the round's GPU budget)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
 
 @pytest.mark.parametrize("name", golden_names("video_frames"))
