@@ -31,7 +31,7 @@ extern "C" {
 #define OVB_ERR_CUDA (-2)
 #define OVB_ERR_UNSUPPORTED_ARCH (-3)
 
-#define OVB_ABI_VERSION 1
+#define OVB_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------- */
 int ovb_abi_version(void);
@@ -326,6 +326,16 @@ typedef struct ovb_conv3d_args {
   const void* resid;      /* bf16, addressed like out, or NULL */
   int32_t out_mode;
   int64_t plane_stride;
+  /* Fused RMS_norm (+SiLU) over the channels of every output voxel (reference vae2_1.py:38-53 followed by
+   * :194-196, the op that consumes nearly every conv output): with norm_gamma (fp32 [Cout], 16-byte
+   * aligned) set, norm_out — addressed like out — receives
+   *     act( v / max(||v||_2, 1e-12) * sqrt(Cout) * gamma ),   v = the bf16 value `out` gets,
+   * in addition to `out`; norm_out == NULL: only the normalised tensor is written, into `out`.
+   * Needs OVB_CONV_OUT_BF16, n_group == 0, Cout == w_rows, Cout % 32 == 0 and Cout <= 256 with
+   * 256 % ... i.e. all channels in ONE N tile (Cout in {32, 64, 96, 128, 192, 256}). */
+  const float* norm_gamma;
+  void* norm_out;
+  int32_t norm_silu;
 } ovb_conv3d_args;
 
 int ovb_conv3d(const ovb_conv3d_args* args, void* stream);

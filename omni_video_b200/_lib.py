@@ -94,6 +94,7 @@ class ConvArgs(C.Structure):
         ("n_group", C.c_int32), ("group_stride", C.c_int64),
         ("resid", C.c_void_p),
         ("out_mode", C.c_int32), ("plane_stride", C.c_int64),
+        ("norm_gamma", C.c_void_p), ("norm_out", C.c_void_p), ("norm_silu", C.c_int32),
     ]
 
 

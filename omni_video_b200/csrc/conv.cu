@@ -30,6 +30,7 @@
 // which lets the same kernel (a) write a 2x nearest-upsampled phase (os_h, os_w doubled, one launch
 // per phase with phase-specific 2x2 taps) and (b) interleave the two channel halves of
 // upsample3d's time_conv as consecutive frames (vae2_1.py:133-136).
+#include <stdlib.h>
 #include <string.h>
 
 #include "host_util.h"
@@ -61,12 +62,23 @@ struct ConvParams {
   long long group_stride;
   int out_mode;
   long long plane_stride;
+  // fused RMS_norm(+SiLU) over the channels of every output voxel (needs the whole channel range in
+  // one N tile): norm_out (or, when null, out itself) receives act(v / max(|v|_2, 1e-12) * sqrt(C) * gamma)
+  const float* norm_gamma;
+  __nv_bfloat16* norm_out;
+  int norm_silu;
   signed char dt[kConvMaxTaps], dh[kConvMaxTaps], dw[kConvMaxTaps];
+  // Brick mode (stride-1 convs whose taps come in (dh0, dh0+1, dh0+2) triples sharing (dt, dw)): one
+  // A load per triple fetches bh+2 input rows, and the three taps' A tiles are that brick read at row
+  // offsets 0, bw, 2*bw — atom-aligned (bw % 8 == 0), so plain descriptor start-address offsets do it.
+  int brick, n_groups, a_rows;
+  signed char g_dt[9], g_dw[9], g_dh0[9];
+  unsigned char g_tap[9][3];
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const ConvParams p) {
+                    const ConvParams p) {  // tmA: box of 128 voxels, or (brick mode) of bw x (bh+2) voxels
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -86,9 +98,9 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m_pairs = (m_tiles + 1) >> 1;
   const int num_tiles = m_pairs * p.n_nt;  // pair tiles (256 voxels x BN)
   const int stages_per_tap = p.n_kc / p.kc_per_stage;
-  const int num_ks = p.n_taps * stages_per_tap;
+  const int num_ks = p.brick ? p.n_groups : p.n_taps * stages_per_tap;
   const int bw = 1 << p.bw_log2;
-  const int a_stage_bytes = p.kc_per_stage * p.a_chunk_bytes;
+  const int a_stage_bytes = (p.brick ? p.n_kc : p.kc_per_stage) * p.a_chunk_bytes;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -125,6 +137,23 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int ht = m % p.n_ht;
         const int t = real ? m / p.n_ht : p.To + 4;  // odd tail: a box fully outside -> zero fill
         const int w0 = (wt << p.bw_log2) * p.sw, h0 = ht * p.bh * p.sh, t0 = t * p.st;
+        if (p.brick) {
+          const uint32_t txb = static_cast<uint32_t>(2 * p.n_kc * p.a_rows * p.KC * 2);
+          for (int g = 0; g < p.n_groups; ++g) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * p.stage_bytes;
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], txb);
+            for (int q = 0; q < p.n_kc; ++q)
+              tma_load_4d_pair(sa + q * p.a_chunk_bytes, &tmA, leader_full, q * p.KC, w0 + p.g_dw[g],
+                               h0 + p.g_dh0[g], t0 + p.g_dt[g]);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const int ct = t0 + p.dt[tap], ch = h0 + p.dh[tap], cw = w0 + p.dw[tap];
           for (int g = 0; g < stages_per_tap; ++g) {
@@ -153,6 +182,24 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int nt = tile % p.n_nt;
         const int wrow0 = nt * p.BN + static_cast<int>(rank) * half;
+        if (p.brick) {
+          const uint32_t txb = static_cast<uint32_t>(2 * 3 * p.n_kc * half * p.KC * 2);
+          for (int g = 0; g < p.n_groups; ++g) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sb = smem + stage * p.stage_bytes + a_stage_bytes;
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], txb);
+            for (int i = 0; i < 3; ++i)
+              for (int q = 0; q < p.n_kc; ++q)
+                tma_load_2d_pair(sb + (i * p.n_kc + q) * p.b_chunk_bytes, &tmB, leader_full,
+                                 p.g_tap[g][i] * p.Cin + q * p.KC, wrow0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.n_taps; ++tap) {
           for (int g = 0; g < stages_per_tap; ++g) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -189,6 +236,16 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
           const uint32_t sb = sa + a_stage_bytes;
+          if (p.brick) {
+            const uint32_t tap_rows = static_cast<uint32_t>(row_bytes) << p.bw_log2;  // bw rows down the brick
+            for (int i = 0; i < 3; ++i)
+              for (int q = 0; q < p.n_kc; ++q)
+                for (int k = 0; k < k_steps; ++k)
+                  umma_ss_pair(d_tmem,
+                               umma_desc_kmajor(sa + q * p.a_chunk_bytes + i * tap_rows + k * 32, row_bytes),
+                               umma_desc_kmajor(sb + (i * p.n_kc + q) * p.b_chunk_bytes + k * 32, row_bytes),
+                               idesc, (ks | i | q | k) != 0);
+          } else
           for (int q = 0; q < p.kc_per_stage; ++q) {
             for (int k = 0; k < k_steps; ++k) {
               umma_ss_pair(d_tmem, umma_desc_kmajor(sa + q * p.a_chunk_bytes + k * 32, row_bytes),
@@ -232,8 +289,16 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (transposed) {
         // 32-column chunks through a swizzled shared-memory transpose (as in gemm.cu): in the read
         // phase 8 lanes cover 64 contiguous output bytes of one voxel and a warp instruction 4
-        // voxels, instead of 32 voxels x 32 bytes
+        // voxels, instead of 32 voxels x 32 bytes.
+        // With a fused RMS_norm the tile is walked twice: pass 0 only accumulates every voxel's sum
+        // of squares (of the bf16-rounded values the unfused formulation would have stored), pass 1
+        // recomputes the values from TMEM and writes them normalised.
         const int n_chunks = p.BN / 32;
+        const bool do_norm = p.norm_gamma != nullptr;
+        float ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float sqrt_c = sqrtf(static_cast<float>(p.Cout));
+#pragma unroll 1
+        for (int pass = do_norm ? 0 : 1; pass < 2; ++pass) {
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c) {
           const int n0 = nt * p.BN + c * 32;
@@ -261,6 +326,11 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float4 bv = *reinterpret_cast<const float4*>(p.bias + col);
             b4[0] = bv.x; b4[1] = bv.y; b4[2] = bv.z; b4[3] = bv.w;
           }
+          float g4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (do_norm && pass == 1 && col_ok) {
+            const float4 gv = *reinterpret_cast<const float4*>(p.norm_gamma + col);
+            g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
+          }
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -281,21 +351,49 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                          : "memory");
             float f0 = __uint_as_float(u0) + b4[0], f1 = __uint_as_float(u1) + b4[1];
             float f2 = __uint_as_float(u2) + b4[2], f3 = __uint_as_float(u3) + b4[3];
-            if (voff[i] >= 0) {
-              if (p.resid != nullptr) {
-                const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].x));
-                const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].y));
-                // conv result is stored as bf16 before the add in the unfused formulation
-                f0 = bf16_round(f0) + a0.x; f1 = bf16_round(f1) + a0.y;
-                f2 = bf16_round(f2) + a1.x; f3 = bf16_round(f3) + a1.y;
-              }
+            if (p.resid != nullptr) {
+              const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].x));
+              const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].y));
+              // conv result is stored as bf16 before the add in the unfused formulation
+              f0 = bf16_round(f0) + a0.x; f1 = bf16_round(f1) + a0.y;
+              f2 = bf16_round(f2) + a1.x; f3 = bf16_round(f3) + a1.y;
+            }
+            if (pass == 0) {
+              // the 8 lanes that share this voxel (cj = lane & 7) add up their 4 columns each
+              const float r0 = bf16_round(f0), r1 = bf16_round(f1), r2 = bf16_round(f2), r3 = bf16_round(f3);
+              float sq = col_ok ? (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3) : 0.f;
+              sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+              sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+              sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+              ss[i] += sq;
+            } else if (voff[i] >= 0) {
               uint2 o;
               o.x = pack_bf16x2(f0, f1);
               o.y = pack_bf16x2(f2, f3);
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + voff[i]) = o;
+              if (!do_norm || p.norm_out != nullptr)
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + voff[i]) = o;
+              if (do_norm) {
+                const float inv = sqrt_c / fmaxf(sqrtf(ss[i]), 1e-12f);
+                float y[4] = {bf16_round(f0) * inv * g4[0], bf16_round(f1) * inv * g4[1],
+                              bf16_round(f2) * inv * g4[2], bf16_round(f3) * inv * g4[3]};
+                if (p.norm_silu) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {  // SiLU(y) = h + h tanh(h), h = y/2 (as rmsnorm_silu_cl_kernel)
+                    const float h = 0.5f * y[j];
+                    float th;
+                    asm("tanh.approx.f32 %0, %1;\n" : "=f"(th) : "f"(h));
+                    y[j] = fmaf(h, th, h);
+                  }
+                }
+                o.x = pack_bf16x2(y[0], y[1]);
+                o.y = pack_bf16x2(y[2], y[3]);
+                __nv_bfloat16* dst = p.norm_out != nullptr ? p.norm_out : reinterpret_cast<__nv_bfloat16*>(p.out);
+                *reinterpret_cast<uint2*>(dst + voff[i]) = o;
+              }
             }
           }
           __syncwarp();
+        }
         }
       } else {
         const int hl = r >> p.bw_log2, wl = r & (bw - 1);
@@ -431,9 +529,6 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
       }
     }
   }
-  const int bw = 1 << p.bw_log2;
-  p.n_wt = (a->Wo + bw - 1) / bw;
-  p.n_ht = (a->Ho + p.bh - 1) / p.bh;
   // ---- K chunk
   p.Cin = a->Cin;
   p.KC = a->Cin % 64 == 0 ? 64 : (a->Cin % 32 == 0 ? 32 : 16);
@@ -442,6 +537,49 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
   for (int i = 0; i < a->n_taps; ++i) {
     p.dt[i] = a->tap_dt[i]; p.dh[i] = a->tap_dh[i]; p.dw[i] = a->tap_dw[i];
   }
+  // ---- brick mode: do the taps come in (dh0, dh0+1, dh0+2) triples that share (dt, dw)?
+  bool brick_taps = a->st == 1 && a->sh == 1 && a->sw == 1 && a->n_taps % 3 == 0 && a->n_taps <= 27 &&
+                    getenv("OVB_CONV_NO_BRICK") == nullptr;
+  if (brick_taps) {
+    bool used[kConvMaxTaps] = {};
+    int ng = 0;
+    for (int i = 0; i < a->n_taps && brick_taps; ++i) {
+      if (used[i]) continue;
+      // i must be the top tap (smallest dh) of its triple
+      int idx[3] = {i, -1, -1};
+      for (int j = 0; j < a->n_taps; ++j) {
+        if (used[j] || j == i || p.dt[j] != p.dt[i] || p.dw[j] != p.dw[i]) continue;
+        if (p.dh[j] == p.dh[i] + 1) idx[1] = j;
+        if (p.dh[j] == p.dh[i] + 2) idx[2] = j;
+        if (p.dh[j] < p.dh[i]) idx[0] = -1;  // not the top tap: handled when its top tap comes up
+      }
+      if (idx[0] < 0) continue;
+      if (idx[1] < 0 || idx[2] < 0 || ng >= 9) { brick_taps = false; break; }
+      p.g_dt[ng] = p.dt[i]; p.g_dw[ng] = p.dw[i]; p.g_dh0[ng] = p.dh[i];
+      for (int u = 0; u < 3; ++u) { p.g_tap[ng][u] = static_cast<unsigned char>(idx[u]); used[idx[u]] = true; }
+      ++ng;
+    }
+    for (int i = 0; i < a->n_taps && brick_taps; ++i) brick_taps = used[i];
+    p.n_groups = ng;
+    if (ng * 3 != a->n_taps) brick_taps = false;
+  }
+  if (brick_taps) {
+    // tallest box (least halo overhead (bh+2)/bh) among the shapes within 2 % of the least padding waste
+    long long best_cover = -1;
+    for (int l2 = 7; l2 >= 3; --l2) {
+      const int bwc = 1 << l2, bhc = 128 >> l2;
+      const long long cover = static_cast<long long>((a->Wo + bwc - 1) / bwc) * bwc * ((a->Ho + bhc - 1) / bhc) * bhc;
+      if (best_cover < 0 || cover < best_cover) best_cover = cover;
+    }
+    for (int l2 = 3; l2 <= 7; ++l2) {
+      const int bwc = 1 << l2, bhc = 128 >> l2;
+      const long long cover = static_cast<long long>((a->Wo + bwc - 1) / bwc) * bwc * ((a->Ho + bhc - 1) / bhc) * bhc;
+      if (cover * 100 <= best_cover * 102) { p.bw_log2 = l2; p.bh = bhc; break; }
+    }
+  }
+  const int bw = 1 << p.bw_log2;
+  p.n_wt = (a->Wo + bw - 1) / bw;
+  p.n_ht = (a->Ho + p.bh - 1) / p.bh;
   // ---- N tile
   p.Cout = a->Cout;
   {
@@ -468,6 +606,25 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
   }
   p.stage_bytes = p.kc_per_stage * chunk_bytes;
   p.stages = ring_budget / p.stage_bytes;
+  p.a_rows = 128;
+  if (brick_taps) {
+    // one stage = one tap triple, all channel chunks: A brick of (bh+2) x bw voxels + 3 taps of weights
+    const int a_rows = (p.bh + 2) * bw;
+    const int a_chunk = (a_rows * p.KC * 2 + 1023) / 1024 * 1024;
+    const int stage = p.n_kc * a_chunk + 3 * p.n_kc * p.b_chunk_bytes;
+    if (ring_budget / stage >= 3) {
+      p.brick = 1;
+      p.a_rows = a_rows;
+      p.a_chunk_bytes = a_chunk;
+      p.kc_per_stage = p.n_kc;
+      p.stage_bytes = stage;
+      p.stages = ring_budget / stage;
+    }
+  }
+  if (!p.brick) {
+    // (the box shape chosen for brick mode is still a valid 128-voxel box)
+    p.n_groups = 0;
+  }
   if (p.stages > kConvMaxStages) p.stages = kConvMaxStages;
   OVB_CHECK_ARG(p.stages >= 2, "ovb_conv3d: tile does not fit shared memory (BN=%d KC=%d)", p.BN, p.KC);
   p.bias = a->bias;
@@ -479,6 +636,20 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
   if (p.n_group == 0) p.n_group = 1 << 30;  // n / n_group == 0 for every n
   p.out_mode = a->out_mode;
   p.plane_stride = a->plane_stride;
+  p.norm_gamma = a->norm_gamma;
+  p.norm_out = reinterpret_cast<__nv_bfloat16*>(a->norm_out);
+  p.norm_silu = a->norm_silu;
+  if (a->norm_gamma != nullptr) {
+    OVB_CHECK_ARG(a->out_mode == OVB_CONV_OUT_BF16 && p.n_nt == 1 && p.BN % 32 == 0 && a->n_group == 0 &&
+                      a->Cout == a->w_rows,
+                  "ovb_conv3d: the fused RMS_norm needs bf16 output, no channel groups and all %d channels in "
+                  "one N tile (BN=%d, tiles=%d)", a->Cout, p.BN, p.n_nt);
+    OVB_CHECK_ARG(reinterpret_cast<uintptr_t>(a->norm_gamma) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(a->norm_out) % 16 == 0,
+                  "ovb_conv3d: norm_gamma / norm_out must be 16-byte aligned");
+  } else {
+    OVB_CHECK_ARG(a->norm_out == nullptr, "ovb_conv3d: norm_out without norm_gamma");
+  }
 
   CUtensorMap tmA, tmB;
   {
@@ -489,7 +660,7 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
                                  static_cast<uint64_t>(a->Cin) * 2 * a->Wi * a->Hi};
     // with an element stride s the box spans s*n source elements and delivers n of them
     const uint32_t box[4] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(bw * a->sw),
-                             static_cast<uint32_t>(p.bh * a->sh), 1};
+                             static_cast<uint32_t>((p.brick ? p.bh + 2 : p.bh) * a->sh), 1};
     const uint32_t estr[4] = {1, static_cast<uint32_t>(a->sw), static_cast<uint32_t>(a->sh), 1};
     OVB_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "ovb_conv3d: strided box too large");
     int rc = encode_tmap_bf16_ex(&tmA, a->x, 4, dims, strides, box, estr, p.KC * 2);

@@ -35,7 +35,7 @@ if has ncu; then
 fi
 if has ncuk; then
   # single-kernel full captures (scripts/ncu_target.py): attention, GEMM (+fp32 residual epilogue), VAE conv, VAE norm
-  for k in attn gemm gemm_resid conv96 conv192 norm; do
+  for k in ${NCU_TARGETS:-attn_b2 gemm gemm_resid conv96 conv192 norm ln rope}; do
     python scripts/ncu_target.py $k > gpurun_out/plain_$k.log 2>&1 &&
     ncu --set full --clock-control none --import-source on --profile-from-start off -f \
         -o gpurun_out/prof_$k python scripts/ncu_target.py $k > gpurun_out/ncu_$k.log 2>&1

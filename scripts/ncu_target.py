@@ -1,5 +1,5 @@
 """Small single-kernel targets for `ncu --set full` captures.
-    python scripts/ncu_target.py attn|gemm|gemm_resid|conv96|conv192|norm
+    python scripts/ncu_target.py attn|attn_b2|gemm|gemm_resid|conv96|conv192|norm|ln|rope
 """
 import math
 import os
@@ -14,9 +14,10 @@ from omni_video_b200 import ops, vae_ops  # noqa: E402
 bf16 = torch.bfloat16
 what = sys.argv[1] if len(sys.argv) > 1 else "attn"
 torch.manual_seed(0)
-if what == "attn":
+if what in ("attn", "attn_b2"):
     L, H = 32760, 12
-    q, k, v = (torch.randn(1, L, H, 128, device="cuda").to(bf16) for _ in range(3))
+    B = 2 if what == "attn_b2" else 1      # attn_b2: the launch bench.py times at N = 1 (cond + uncond batched)
+    q, k, v = (torch.randn(B, L, H, 128, device="cuda").to(bf16) for _ in range(3))
     out = torch.empty_like(q)
     fn = lambda: ops.attention(q, k, v, out=out)  # noqa: E731
 elif what in ("gemm", "gemm_resid"):
@@ -38,6 +39,18 @@ elif what in ("conv96", "conv192"):
     wt = torch.randn(c, c, 3, 3, 3, device="cuda") / math.sqrt(27 * c)
     pc = vae_ops.pack_conv3d(wt, torch.zeros(c, device="cuda"))
     fn = lambda: vae_ops.conv3d(x, pc, (T, H, W))  # noqa: E731
+elif what == "ln":
+    L, d = 65520, 1536
+    x = torch.randn(L, d, device="cuda")
+    tbl = torch.randn(2, 6, d, device="cuda")
+    o = torch.empty(L, d, device="cuda", dtype=bf16)
+    fn = lambda: ops.layernorm_modulate(x, tbl[:, 1], tbl[:, 0], 1e-6, rows_per_sample=32760, out=o)  # noqa: E731
+elif what == "rope":
+    L, d = 65520, 1536
+    qkv = torch.randn(L, 3 * d, device="cuda").to(bf16)
+    w = torch.ones(d, device="cuda", dtype=bf16)
+    cs = ops.rope_cos_sin_table().cuda()
+    fn = lambda: ops.rmsnorm_rope_(qkv[:, :d], w, 1e-6, cs_table=cs, grid=(21, 30, 52), rows_per_sample=32760)  # noqa: E731
 else:
     x = torch.randn(9 * 480 * 832, 96, device="cuda").to(bf16)
     g = torch.ones(96, device="cuda")
