@@ -9,9 +9,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libovb200.so")
+# OVB_LIB_PATH: load another build of the same ABI (kernel experiments: scripts/build_variant_lib.sh)
+LIB_PATH = os.environ.get("OVB_LIB_PATH") or os.path.join(_HERE, "libovb200.so")
 
 OVB_OK = 0
+ABI_VERSION = 2   # include/ovb200.h OVB_ABI_VERSION
 
 # epilogues / modes (mirror include/ovb200.h)
 EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_GATE_RESID_F32, EPI_F32, EPI_RESID_BF16 = range(6)
@@ -172,8 +174,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.ovb_abi_version() != 1:
-        raise OvbError(f"ABI version mismatch: library {lib.ovb_abi_version()} != binding 1")
+    if lib.ovb_abi_version() != ABI_VERSION:
+        raise OvbError(f"ABI version mismatch: library {lib.ovb_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -223,6 +223,19 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t idesc = umma_idesc_bf16(256, p.BN, 0, 0);
       const uint32_t row_bytes = p.KC * 2;
       const int k_steps = p.KC / 16;
+      // Shared-memory descriptors: everything but the start address is the same for every MMA of the
+      // launch, and all offsets are multiples of 16 bytes, so one MMA costs one 32-bit add on the
+      // descriptor's low word.  (Rebuilding the descriptor from runtime parameters inside the triple
+      // loop made the ISSUE the bottleneck: ~140 cycles per MMA against a 48-cycle tensor floor at
+      // N = 96.)
+      const uint64_t desc_tmpl = umma_desc_kmajor(0, row_bytes);
+      const uint32_t a_chunk16 = static_cast<uint32_t>(p.a_chunk_bytes) >> 4;
+      const uint32_t b_chunk16 = static_cast<uint32_t>(p.b_chunk_bytes) >> 4;
+      const uint32_t tap_rows16 = (row_bytes << p.bw_log2) >> 4;  // brick mode: bw rows down the brick
+      const int n_kc = p.n_kc, kc_per_stage = p.kc_per_stage, brick = p.brick, n_stages = p.stages;
+      const uint32_t stage16 = static_cast<uint32_t>(p.stage_bytes) >> 4;
+      const uint32_t a_stage16 = static_cast<uint32_t>(a_stage_bytes) >> 4;
+      const uint32_t smem16 = (smem_u32(smem) & 0x3FFFF) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -234,28 +247,38 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int ks = 0; ks < num_ks; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
-          const uint32_t sb = sa + a_stage_bytes;
-          if (p.brick) {
-            const uint32_t tap_rows = static_cast<uint32_t>(row_bytes) << p.bw_log2;  // bw rows down the brick
-            for (int i = 0; i < 3; ++i)
-              for (int q = 0; q < p.n_kc; ++q)
-                for (int k = 0; k < k_steps; ++k)
-                  umma_ss_pair(d_tmem,
-                               umma_desc_kmajor(sa + q * p.a_chunk_bytes + i * tap_rows + k * 32, row_bytes),
-                               umma_desc_kmajor(sb + (i * p.n_kc + q) * p.b_chunk_bytes + k * 32, row_bytes),
-                               idesc, (ks | i | q | k) != 0);
-          } else
-          for (int q = 0; q < p.kc_per_stage; ++q) {
-            for (int k = 0; k < k_steps; ++k) {
-              umma_ss_pair(d_tmem, umma_desc_kmajor(sa + q * p.a_chunk_bytes + k * 32, row_bytes),
-                           umma_desc_kmajor(sb + q * p.b_chunk_bytes + k * 32, row_bytes), idesc,
-                           (ks | q | k) != 0);
+          const uint32_t sa16 = smem16 + stage * stage16;
+          const uint32_t sb16 = sa16 + a_stage16;
+          uint32_t first = ks == 0 ? 0u : 1u;   // accumulate flag of the next MMA
+          if (brick) {
+            for (int i = 0; i < 3; ++i) {
+              uint32_t a16 = sa16 + i * tap_rows16;
+              uint32_t b16 = sb16 + i * n_kc * b_chunk16;
+              for (int q = 0; q < n_kc; ++q) {
+                for (int k = 0; k < k_steps; ++k) {
+                  umma_ss_pair(d_tmem, desc_tmpl | ((a16 + 2 * k) & 0x3FFFu), desc_tmpl | ((b16 + 2 * k) & 0x3FFFu), idesc,
+                               first);
+                  first = 1u;
+                }
+                a16 += a_chunk16;
+                b16 += b_chunk16;
+              }
+            }
+          } else {
+            uint32_t a16 = sa16, b16 = sb16;
+            for (int q = 0; q < kc_per_stage; ++q) {
+              for (int k = 0; k < k_steps; ++k) {
+                umma_ss_pair(d_tmem, desc_tmpl | ((a16 + 2 * k) & 0x3FFFu), desc_tmpl | ((b16 + 2 * k) & 0x3FFFu), idesc,
+                               first);
+                first = 1u;
+              }
+              a16 += a_chunk16;
+              b16 += b_chunk16;
             }
           }
           umma_commit_pair(&empty_bar[stage], 3);
           if (ks == num_ks - 1) umma_commit_pair(&tfull_bar[acc], 3);
-          if (++stage == p.stages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -286,6 +309,12 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int t = m / p.n_ht;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+#ifndef OVB_CONV_DBG
+#define OVB_CONV_DBG 0
+#endif
+      if (OVB_CONV_DBG == 2) {
+        // experiment: no epilogue at all (results are garbage): the main loop alone
+      } else
       if (transposed) {
         // 32-column chunks through a swizzled shared-memory transpose (as in gemm.cu): in the read
         // phase 8 lanes cover 64 contiguous output bytes of one voxel and a warp instruction 4
@@ -293,43 +322,43 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // With a fused RMS_norm the tile is walked twice: pass 0 only accumulates every voxel's sum
         // of squares (of the bf16-rounded values the unfused formulation would have stored), pass 1
         // recomputes the values from TMEM and writes them normalised.
+        // One epilogue warp per scheduler executes this alone, at ~3-4 cycles per dependent
+        // instruction: the instruction COUNT is what has to stay below the main loop's duration, so
+        // everything that does not depend on the chunk is computed once per tile.
         const int n_chunks = p.BN / 32;
         const bool do_norm = p.norm_gamma != nullptr;
-        float ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const float sqrt_c = sqrtf(static_cast<float>(p.Cout));
-#pragma unroll 1
-        for (int pass = do_norm ? 0 : 1; pass < 2; ++pass) {
-#pragma unroll 1
-        for (int c = 0; c < n_chunks; ++c) {
-          const int n0 = nt * p.BN + c * 32;
-          if (n0 >= p.Cout) break;  // warp-uniform
+        const bool has_resid = p.resid != nullptr;
+        __nv_bfloat16* const out_raw = (!do_norm || p.norm_out != nullptr) ? reinterpret_cast<__nv_bfloat16*>(p.out) : nullptr;
+        __nv_bfloat16* const out_nrm = do_norm ? (p.norm_out != nullptr ? p.norm_out : reinterpret_cast<__nv_bfloat16*>(p.out)) : nullptr;
+        // this lane's 8 voxels of the read phase: offset of channel 0, or -1
+        long long vbase[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = quad * 32 + 4 * i + rr_off;
+          const int h = ht * p.bh + (rr >> p.bw_log2), w = (wt << p.bw_log2) + (rr & (bw - 1));
+          vbase[i] = (real && h < p.Ho && w < p.Wo) ? p.out_base + t * p.os_t + h * p.os_h + w * p.os_w : -1;
+        }
+        // chunk c of the accumulator -> the bf16 values of this lane's 8 voxels x 4 columns (bias and
+        // residual applied, packed as the raw tensor holds them)
+        auto chunk_values = [&](const int c, uint2 (&o8)[8], bool& col_ok, long long& coff) {
           uint32_t v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + c * 32, v);
-          const int col = n0 + cj * 4;
-          const bool col_ok = col < p.Cout;
+          const int col = nt * p.BN + c * 32 + cj * 4;
+          col_ok = col < p.Cout;
           const int grp = col / p.n_group;
-          const long long coff = grp * p.group_stride + (col - grp * p.n_group);
-          // this lane's 8 voxels of the read phase and their residual values, requested up front
-          long long voff[8];
-          uint2 xb[8];
+          coff = grp * p.group_stride + (col - grp * p.n_group);
+          uint2 xb[8];  // residual values, requested up front
+          if (has_resid) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = quad * 32 + 4 * i + rr_off;
-            const int h = ht * p.bh + (rr >> p.bw_log2), w = (wt << p.bw_log2) + (rr & (bw - 1));
-            const bool ok = real && col_ok && h < p.Ho && w < p.Wo;
-            voff[i] = ok ? p.out_base + t * p.os_t + h * p.os_h + w * p.os_w + coff : -1;
-            xb[i] = make_uint2(0u, 0u);
-            if (ok && p.resid != nullptr) xb[i] = *reinterpret_cast<const uint2*>(p.resid + voff[i]);
+            for (int i = 0; i < 8; ++i) {
+              xb[i] = make_uint2(0u, 0u);
+              if (col_ok && vbase[i] >= 0) xb[i] = *reinterpret_cast<const uint2*>(p.resid + vbase[i] + coff);
+            }
           }
           float b4[4] = {0.f, 0.f, 0.f, 0.f};
           if (p.bias != nullptr && col_ok) {
             const float4 bv = *reinterpret_cast<const float4*>(p.bias + col);
             b4[0] = bv.x; b4[1] = bv.y; b4[2] = bv.z; b4[3] = bv.w;
-          }
-          float g4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (do_norm && pass == 1 && col_ok) {
-            const float4 gv = *reinterpret_cast<const float4*>(p.norm_gamma + col);
-            g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
           }
           tmem_wait_ld();
 #pragma unroll
@@ -351,49 +380,136 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                          : "memory");
             float f0 = __uint_as_float(u0) + b4[0], f1 = __uint_as_float(u1) + b4[1];
             float f2 = __uint_as_float(u2) + b4[2], f3 = __uint_as_float(u3) + b4[3];
-            if (p.resid != nullptr) {
+            if (has_resid) {
               const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].x));
               const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].y));
               // conv result is stored as bf16 before the add in the unfused formulation
               f0 = bf16_round(f0) + a0.x; f1 = bf16_round(f1) + a0.y;
               f2 = bf16_round(f2) + a1.x; f3 = bf16_round(f3) + a1.y;
             }
-            if (pass == 0) {
-              // the 8 lanes that share this voxel (cj = lane & 7) add up their 4 columns each
-              const float r0 = bf16_round(f0), r1 = bf16_round(f1), r2 = bf16_round(f2), r3 = bf16_round(f3);
-              float sq = col_ok ? (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3) : 0.f;
-              sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-              sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-              sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-              ss[i] += sq;
-            } else if (voff[i] >= 0) {
-              uint2 o;
-              o.x = pack_bf16x2(f0, f1);
-              o.y = pack_bf16x2(f2, f3);
-              if (!do_norm || p.norm_out != nullptr)
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + voff[i]) = o;
-              if (do_norm) {
-                const float inv = sqrt_c / fmaxf(sqrtf(ss[i]), 1e-12f);
-                float y[4] = {bf16_round(f0) * inv * g4[0], bf16_round(f1) * inv * g4[1],
-                              bf16_round(f2) * inv * g4[2], bf16_round(f3) * inv * g4[3]};
-                if (p.norm_silu) {
+            o8[i].x = pack_bf16x2(f0, f1);
+            o8[i].y = pack_bf16x2(f2, f3);
+          }
+          __syncwarp();
+        };
+        // sum of squares of this lane's 4 values of one voxel (the other 7 lanes that share the voxel,
+        // cj = lane & 7, are added once all chunks are in: reduce8)
+        auto sumsq4 = [&](const uint2 o, const bool col_ok) {
+          const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
+          const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.y));
+          return col_ok ? (r01.x * r01.x + r01.y * r01.y) + (r23.x * r23.x + r23.y * r23.y) : 0.f;
+        };
+        auto reduce8 = [&](float sq) {
+          sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+          return sq;
+        };
+        auto normalised = [&](const uint2 o, const float inv, const float (&g4)[4]) {
+          const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
+          const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.y));
+          float y[4] = {r01.x * inv * g4[0], r01.y * inv * g4[1], r23.x * inv * g4[2], r23.y * inv * g4[3]};
+          if (p.norm_silu) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {  // SiLU(y) = h + h tanh(h), h = y/2 (as rmsnorm_silu_cl_kernel)
-                    const float h = 0.5f * y[j];
-                    float th;
-                    asm("tanh.approx.f32 %0, %1;\n" : "=f"(th) : "f"(h));
-                    y[j] = fmaf(h, th, h);
-                  }
-                }
-                o.x = pack_bf16x2(y[0], y[1]);
-                o.y = pack_bf16x2(y[2], y[3]);
-                __nv_bfloat16* dst = p.norm_out != nullptr ? p.norm_out : reinterpret_cast<__nv_bfloat16*>(p.out);
-                *reinterpret_cast<uint2*>(dst + voff[i]) = o;
+            for (int j = 0; j < 4; ++j) {  // SiLU(y) = h + h tanh(h), h = y/2 (as rmsnorm_silu_cl_kernel)
+              const float h = 0.5f * y[j];
+              float th;
+              asm("tanh.approx.f32 %0, %1;\n" : "=f"(th) : "f"(h));
+              y[j] = fmaf(h, th, h);
+            }
+          }
+          uint2 r;
+          r.x = pack_bf16x2(y[0], y[1]);
+          r.y = pack_bf16x2(y[2], y[3]);
+          return r;
+        };
+        auto load_gamma = [&](const int c, float (&g4)[4]) {
+          const int col = nt * p.BN + c * 32 + cj * 4;
+          g4[0] = g4[1] = g4[2] = g4[3] = 0.f;
+          if (col < p.Cout) {
+            const float4 gv = *reinterpret_cast<const float4*>(p.norm_gamma + col);
+            g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
+          }
+        };
+        const float sqrt_c = sqrtf(static_cast<float>(p.Cout));
+        float ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (!do_norm) {
+#pragma unroll 1
+          for (int c = 0; c < n_chunks; ++c) {
+            if (nt * p.BN + c * 32 >= p.Cout) break;  // warp-uniform
+            uint2 o8[8];
+            bool col_ok;
+            long long coff;
+            chunk_values(c, o8, col_ok, coff);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (col_ok && vbase[i] >= 0) *reinterpret_cast<uint2*>(out_raw + vbase[i] + coff) = o8[i];
+          }
+        } else if (n_chunks <= 3) {
+          // <= 96 channels: ONE walk over the accumulator; the bf16 values stay in registers (two per
+          // voxel and chunk) until the voxel's sum of squares is complete
+          uint2 keep[3][8];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (c < n_chunks) {
+              bool col_ok;
+              long long coff;
+              chunk_values(c, keep[c], col_ok, coff);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                ss[i] += sumsq4(keep[c][i], col_ok);
+                if (out_raw != nullptr && col_ok && vbase[i] >= 0)
+                  *reinterpret_cast<uint2*>(out_raw + vbase[i] + coff) = keep[c][i];
               }
             }
           }
-          __syncwarp();
-        }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ss[i] = sqrt_c * rsqrtf(fmaxf(reduce8(ss[i]), 1e-24f));  // sqrt(C) / max(|v|, 1e-12)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (c < n_chunks) {
+              const int col = nt * p.BN + c * 32 + cj * 4;
+              const int grp = col / p.n_group;
+              const long long coff = grp * p.group_stride + (col - grp * p.n_group);
+              float g4[4];
+              load_gamma(c, g4);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (col < p.Cout && vbase[i] >= 0)
+                  *reinterpret_cast<uint2*>(out_nrm + vbase[i] + coff) = normalised(keep[c][i], ss[i], g4);
+            }
+          }
+        } else {
+          // more channels than the registers can keep: the tile is walked twice
+#pragma unroll 1
+          for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ss[i] = sqrt_c * rsqrtf(fmaxf(reduce8(ss[i]), 1e-24f));
+            }
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c) {
+              if (nt * p.BN + c * 32 >= p.Cout) break;  // warp-uniform
+              uint2 o8[8];
+              bool col_ok;
+              long long coff;
+              chunk_values(c, o8, col_ok, coff);
+              if (pass == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ss[i] += sumsq4(o8[i], col_ok);
+              } else {
+                float g4[4];
+                load_gamma(c, g4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (col_ok && vbase[i] >= 0) {
+                    if (out_raw != nullptr) *reinterpret_cast<uint2*>(out_raw + vbase[i] + coff) = o8[i];
+                    *reinterpret_cast<uint2*>(out_nrm + vbase[i] + coff) = normalised(o8[i], ss[i], g4);
+                  }
+                }
+              }
+            }
+          }
         }
       } else {
         const int hl = r >> p.bw_log2, wl = r & (bw - 1);
@@ -571,10 +687,12 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
       const long long cover = static_cast<long long>((a->Wo + bwc - 1) / bwc) * bwc * ((a->Ho + bhc - 1) / bhc) * bhc;
       if (best_cover < 0 || cover < best_cover) best_cover = cover;
     }
-    for (int l2 = 3; l2 <= 7; ++l2) {
+    const char* force = getenv("OVB_CONV_BOX_L2");  // experiments: log2 of the box width
+    const int lo = force != nullptr ? atoi(force) : 3, hi = force != nullptr ? atoi(force) : 7;
+    for (int l2 = lo; l2 <= hi; ++l2) {
       const int bwc = 1 << l2, bhc = 128 >> l2;
       const long long cover = static_cast<long long>((a->Wo + bwc - 1) / bwc) * bwc * ((a->Ho + bhc - 1) / bhc) * bhc;
-      if (cover * 100 <= best_cover * 102) { p.bw_log2 = l2; p.bh = bhc; break; }
+      if (force != nullptr || cover * 100 <= best_cover * 102) { p.bw_log2 = l2; p.bh = bhc; break; }
     }
   }
   const int bw = 1 << p.bw_log2;

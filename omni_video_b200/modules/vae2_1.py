@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 import re
 from typing import Dict, List, Optional
 
@@ -380,20 +381,47 @@ class VAEEngine:
         top, bottom = lo < 0, hi > 0
         return halo_exchange(x, self.strip, top, bottom), (1 if top else 0)
 
-    def _causal_conv(self, x, name, resid=None):
+    def _causal_conv(self, x, name, resid=None, **kw):
         T, H, W, _ = x.shape
         pc = self._conv(name)
         xin, shift = self._halo(x, pc)
-        return vae_ops.conv3d(xin, pc, (T, H, W), resid=resid, dh_shift=shift)
+        return vae_ops.conv3d(xin, pc, (T, H, W), resid=resid, dh_shift=shift, **kw)
 
-    def _residual_block(self, x, p):
+    def _residual_block(self, x, p, x_norm=None, next_gamma=None, raw_needed=True):
+        """reference vae2_1.py:185-219: x + conv(act(norm(conv(act(norm(x)))))) (+ 1x1x1 shortcut).
+        Both RMS_norm·SiLU passes disappear into conv epilogues where one N tile holds all channels
+        (OVB_FUSE_NORM=0 keeps them as separate launches):
+          * residual.3 (norm of the first conv's output, used by nothing else) is applied by that
+            conv's epilogue;
+          * the norm that CONSUMES this block's output (the next block's residual.0, or the decoder/
+            encoder head norm: `next_gamma`) is written by the second conv's epilogue as a second
+            tensor, next to the raw sum the next block needs as its residual input.
+        x_norm: act(norm(x)) already produced by the previous block.  Returns (y, act(norm_next(y)) or
+        None); y is None when the caller declared it unused (raw_needed=False)."""
         sd = self._params()
+        fuse = os.environ.get("OVB_FUSE_NORM", "1") != "0"
         h = self._causal_conv(x, p + "shortcut") if (p + "shortcut.weight") in sd else x
-        a = vae_ops.rmsnorm_silu(x, self._gamma(p + "residual.0.gamma"))
-        b = self._causal_conv(a, p + "residual.2")
+        a = x_norm if x_norm is not None else vae_ops.rmsnorm_silu(x, self._gamma(p + "residual.0.gamma"))
+        g3 = self._gamma(p + "residual.3.gamma")
+        if fuse and vae_ops.can_fuse_norm(self._conv(p + "residual.2")):
+            b = self._causal_conv(a, p + "residual.2", norm_gamma=g3)
+        else:
+            b = self._causal_conv(a, p + "residual.2")
+            vae_ops.rmsnorm_silu(b, g3, out=b)                                  # in place: elementwise
         del a
-        vae_ops.rmsnorm_silu(b, self._gamma(p + "residual.3.gamma"), out=b)     # in place: elementwise
-        return self._causal_conv(b, p + "residual.6", resid=h)
+        pc2 = self._conv(p + "residual.6")
+        # the two-tensor form keeps a tile's values in registers between the statistics and the
+        # normalised store, which only fits up to 96 channels; wider layers keep the separate pass
+        dual_ok = pc2.cout <= 96
+        if (next_gamma is not None and fuse and vae_ops.can_fuse_norm(pc2) and next_gamma.numel() == pc2.cout
+                and (dual_ok or not raw_needed)):
+            if raw_needed:
+                yn = torch.empty((x.shape[0], x.shape[1], x.shape[2], pc2.cout), device=x.device, dtype=bf16)
+                y = self._causal_conv(b, p + "residual.6", resid=h, norm_gamma=next_gamma, norm_out=yn)
+                return y, yn
+            return None, self._causal_conv(b, p + "residual.6", resid=h, norm_gamma=next_gamma)
+        y = self._causal_conv(b, p + "residual.6", resid=h)
+        return y, None
 
     def _attention_block(self, x, p):
         T, H, W, Cc = x.shape
@@ -484,15 +512,31 @@ class VAEEngine:
             x = y
         return x
 
-    def _stack(self, x, prefix, up: bool):
+    def _stack(self, x, prefix, up: bool, tail_gamma=None):
+        """Runs the numbered modules under `prefix`.  tail_gamma: gamma of the RMS_norm·SiLU that follows
+        the stack and is the ONLY consumer of its output (the head norm): when the last module is a
+        residual block whose conv can fuse it, the stack returns that normalised tensor and the caller
+        skips the norm (`self._tail_fused` tells)."""
         sd = self._params()
         pat = re.compile(re.escape(prefix) + r"(\d+)\.")
         idx = sorted({int(mm.group(1)) for k in sd for mm in [pat.match(k)] if mm})
-        for i in idx:
+        x_norm = None                      # act(norm(x)) for the next residual block, if already made
+        self._tail_fused = False
+        for n, i in enumerate(idx):
             p = f"{prefix}{i}."
             if (p + "residual.2.weight") in sd:
-                x = self._residual_block(x, p)
-            elif (p + "to_qkv.weight") in sd:
+                nxt = f"{prefix}{idx[n + 1]}." if n + 1 < len(idx) else None
+                if nxt is not None and (nxt + "residual.0.gamma") in sd:
+                    x, x_norm = self._residual_block(x, p, x_norm, self._gamma(nxt + "residual.0.gamma"))
+                elif nxt is None and tail_gamma is not None:
+                    y, yn = self._residual_block(x, p, x_norm, tail_gamma, raw_needed=False)
+                    x, x_norm = (yn, None) if yn is not None else (y, None)
+                    self._tail_fused = yn is not None
+                else:
+                    x, x_norm = self._residual_block(x, p, x_norm)
+                continue
+            x_norm = None
+            if (p + "to_qkv.weight") in sd:
                 x = self._attention_block(x, p)
             elif (p + "resample.1.weight") in sd:
                 three_d = (p + "time_conv.weight") in sd
@@ -520,8 +564,10 @@ class VAEEngine:
             x = vae_ops.conv3d(x, self._conv("conv2"), (T, H, W))                # 1x1x1 (:552)
             x = self._causal_conv(x, "decoder.conv1")
             x = self._stack(x, "decoder.middle.", up=True)
-            x = self._stack(x, "decoder.upsamples.", up=True)
-            vae_ops.rmsnorm_silu(x, self._gamma("decoder.head.0.gamma"), out=x)
+            head_gamma = self._gamma("decoder.head.0.gamma")
+            x = self._stack(x, "decoder.upsamples.", up=True, tail_gamma=head_gamma)
+            if not self._tail_fused:
+                vae_ops.rmsnorm_silu(x, head_gamma, out=x)
             T, H, W, _ = x.shape
             out = torch.empty((3, T, H, W), device=self.dev, dtype=f32)
             pc_head = self._conv("decoder.head.2")
@@ -553,8 +599,10 @@ class VAEEngine:
             x = vae_ops.planar_to_cl(v, self._ones[3], self._zeros[3], 16)
             x = self._causal_conv(x, "encoder.conv1")
             x = self._stack(x, "encoder.downsamples.", up=False)
-            x = self._stack(x, "encoder.middle.", up=False)
-            vae_ops.rmsnorm_silu(x, self._gamma("encoder.head.0.gamma"), out=x)
+            head_gamma = self._gamma("encoder.head.0.gamma")
+            x = self._stack(x, "encoder.middle.", up=False, tail_gamma=head_gamma)
+            if not self._tail_fused:
+                vae_ops.rmsnorm_silu(x, head_gamma, out=x)
             x = self._causal_conv(x, "encoder.head.2")                            # [T', h, w, 32]
             T, H, W, _ = x.shape
             x = vae_ops.conv3d(x, self._conv("conv1"), (T, H, W))                # 1x1x1 (:534)

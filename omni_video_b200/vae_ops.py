@@ -105,10 +105,14 @@ def conv3d(x: torch.Tensor, pc: PackedConv, out_extent: Tuple[int, int, int], *,
            out: Optional[torch.Tensor] = None, out_strides: Optional[Tuple[int, int, int]] = None,
            out_base: int = 0, n_group: int = 0, group_stride: int = 0,
            resid: Optional[torch.Tensor] = None, out_mode: int = CONV_OUT_BF16,
-           plane_stride: int = 0, dh_shift: int = 0) -> torch.Tensor:
+           plane_stride: int = 0, dh_shift: int = 0, norm_gamma: Optional[torch.Tensor] = None,
+           norm_out: Optional[torch.Tensor] = None, norm_silu: bool = True) -> torch.Tensor:
     """x: bf16 [Ti, Hi, Wi, Cin] contiguous.  Default output: a new bf16 [To, Ho, Wo, Cout].
     dh_shift is added to every tap's row offset (a strip whose input carries `dh_shift` halo rows
-    on top)."""
+    on top).
+    norm_gamma (fp32 [Cout]): fuse the RMS_norm (+SiLU) that consumes this conv's output into the
+    epilogue (`can_fuse_norm(pc)` must hold).  Without norm_out the returned tensor IS the normalised
+    one; with norm_out (bf16, shaped like the output) the raw output is returned and norm_out filled."""
     _need_cuda(x, pc.w, out, resid)
     lib = _lib.load()
     assert x.dtype == bf16 and x.dim() == 4 and x.is_contiguous(), "x must be contiguous bf16 [T,H,W,C]"
@@ -138,10 +142,27 @@ def conv3d(x: torch.Tensor, pc: PackedConv, out_extent: Tuple[int, int, int], *,
         assert resid.dtype == bf16 and resid.is_contiguous() and resid.numel() == out.numel()
         a.resid = resid.data_ptr()
     a.out_mode, a.plane_stride = out_mode, plane_stride
+    if norm_gamma is not None:
+        assert can_fuse_norm(pc), f"RMS_norm cannot be fused into a conv with {pc.cout} output channels"
+        assert norm_gamma.dtype == f32 and norm_gamma.is_contiguous() and norm_gamma.numel() == pc.cout
+        _need_cuda(norm_gamma, norm_out)
+        a.norm_gamma, a.norm_silu = norm_gamma.data_ptr(), int(norm_silu)
+        if norm_out is not None:
+            assert norm_out.dtype == bf16 and norm_out.is_contiguous() and norm_out.numel() == out.numel()
+            a.norm_out = norm_out.data_ptr()
+    else:
+        assert norm_out is None
     ev = ops_mod._tl_begin()
     _lib.check(lib.ovb_conv3d(C.byref(a), _stream()), "ovb_conv3d")
     ops_mod._tl_end(ev, "conv", 2.0 * To * Ho * Wo * pc.cout * pc.n_taps * Cin, (To, Ho, Wo, Cin, pc.cout, pc.n_taps))
     return out
+
+
+def can_fuse_norm(pc: PackedConv) -> bool:
+    """The conv epilogue can apply the following RMS_norm when one N tile holds every output channel
+    (ovb_conv3d picks the largest multiple of 16 <= 256 dividing the weight rows as tile width)."""
+    rows = pc.w.shape[0]
+    return rows == pc.cout and rows <= 256 and rows % 32 == 0
 
 
 def rmsnorm_silu(x: torch.Tensor, gamma: torch.Tensor, silu: bool = True,

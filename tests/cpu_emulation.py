@@ -166,7 +166,7 @@ def install(monkeypatch):
 
 # ------------------------------------------------------------------------------------------------- VAE
 def conv3d(x, pc, out_extent, *, out=None, out_strides=None, out_base=0, n_group=0, group_stride=0, resid=None,
-           out_mode=0, plane_stride=0, dh_shift=0):
+           out_mode=0, plane_stride=0, dh_shift=0, norm_gamma=None, norm_out=None, norm_silu=True):
     """ovb_conv3d (include/ovb200.h): taps with zero fill outside x, bias, optional bf16 residual (the conv result
     is rounded to bf16 before the add), output scattered through (os_t, os_h, os_w, out_base, n_group)."""
     from omni_video_b200 import vae_ops
@@ -200,6 +200,13 @@ def conv3d(x, pc, out_extent, *, out=None, out_strides=None, out_base=0, n_group
         y = acc
         if resid is not None:
             y = _rb(y) + resid.reshape(-1)[idx].float().view_as(y)
+        if norm_gamma is not None:
+            # fused RMS_norm (+SiLU) of the bf16 value the unfused formulation would have stored
+            yn = rmsnorm_silu(y.to(bf16), norm_gamma, silu=norm_silu)
+            if norm_out is None:
+                out.view(-1)[idx] = yn.reshape(-1)
+                return out
+            norm_out.view(-1)[idx] = yn.reshape(-1)
         out.view(-1)[idx] = y.to(bf16).reshape(-1)
         return out
     idx = (base.unsqueeze(-1) + (n * plane_stride).view(1, 1, 1, -1)).reshape(-1)

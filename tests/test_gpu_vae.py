@@ -64,6 +64,60 @@ def test_causal_conv3d_3x3x3(vops, cin, cout, T, H, W):
     _close(_planar(y), ref.to(bf16).float())
 
 
+@pytest.mark.parametrize("c,T,H,W,with_resid,dual", [(96, 2, 9, 20, False, False), (96, 3, 16, 24, True, True),
+                                                      (192, 2, 8, 16, True, False), (32, 1, 5, 9, False, True)])
+def test_conv_with_fused_rmsnorm_silu(vops, c, T, H, W, with_resid, dual):
+    """The conv epilogue applies the RMS_norm·SiLU that consumes its output (reference vae2_1.py:38-53,
+    :194-196): same result as conv followed by ovb_rmsnorm_silu_cl, for the single-output form (only the
+    normalised tensor is kept) and the dual form (raw sum + normalised tensor)."""
+    rng = _rng(7 * c + T)
+    x = _randn(rng, c, T, H, W).to(bf16).float()
+    w = _randn(rng, c, c, 3, 3, 3, scale=1.0 / (27 * c) ** 0.5).to(bf16).float()
+    b = _randn(rng, c, scale=0.1)
+    gamma = (1.0 + _randn(rng, c, scale=0.1)).cuda()
+    res = _cl(_randn(rng, c, T, H, W)) if with_resid else None
+    pc = vops.pack_conv3d(w.cuda(), b.cuda())
+    assert vops.can_fuse_norm(pc)
+    raw = vops.conv3d(_cl(x), pc, (T, H, W), resid=res)
+    ref_n = vops.rmsnorm_silu(raw, gamma)
+    if dual:
+        yn = torch.empty_like(raw)
+        y = vops.conv3d(_cl(x), pc, (T, H, W), resid=res, norm_gamma=gamma, norm_out=yn)
+        assert torch.equal(y, raw)
+    else:
+        yn = vops.conv3d(_cl(x), pc, (T, H, W), resid=res, norm_gamma=gamma)
+    # the two differ only in the summation order of the squares (and then by at most one bf16 ulp)
+    d = (yn.float() - ref_n.float()).abs()
+    assert d.max().item() <= 2 ** -7 * max(1.0, ref_n.float().abs().max().item())
+    assert (d > 0).float().mean().item() < 0.02
+    # and against the fp32 oracle composition
+    ref = V.causal_conv3d(x, w, b).to(bf16).float()
+    if with_resid:
+        ref = (ref + _planar(res)).to(bf16).float()
+    refn = V.rms_norm(ref, gamma.cpu().view(c, 1, 1, 1), silu=True)
+    _close(_planar(yn), refn.to(bf16).float())
+
+
+def test_conv_brick_mode_matches_tap_mode(vops, monkeypatch):
+    """3x3x3 stride-1 convs fetch one (bh+2)-row brick per (dt, dw) instead of one box per tap; results
+    are the same products accumulated in another tap order: equal to the per-tap path (OVB_CONV_NO_BRICK=1)
+    up to fp32 accumulation order, i.e. a rare last-bit difference after the bf16 rounding."""
+    rng = _rng(11)
+    for cin, cout, T, H, W in [(96, 96, 3, 40, 72), (96, 16, 2, 33, 50), (16, 384, 2, 12, 20)]:
+        x = _cl(_randn(rng, cin, T, H, W))
+        w = _randn(rng, cout, cin, 3, 3, 3, scale=1.0 / (27 * cin) ** 0.5)
+        pc = vops.pack_conv3d(w.cuda(), _randn(rng, cout, scale=0.1).cuda())
+        monkeypatch.delenv("OVB_CONV_NO_BRICK", raising=False)
+        a = vops.conv3d(x, pc, (T, H, W))
+        monkeypatch.setenv("OVB_CONV_NO_BRICK", "1")
+        b = vops.conv3d(x, pc, (T, H, W))
+        monkeypatch.delenv("OVB_CONV_NO_BRICK", raising=False)
+        # same products, summed in another tap order: fp32 accumulation-order differences only
+        d = (a.float() - b.float()).abs()
+        assert d.max().item() <= 2 ** -7 * max(1.0, b.float().abs().max().item()), (cin, cout)
+        assert (d > 0).float().mean().item() < 0.05, (cin, cout)
+
+
 def test_conv_1x1x1_time_conv_and_residual(vops):
     rng = _rng(3)
     cin, cout, T, H, W = 192, 384, 3, 7, 12
