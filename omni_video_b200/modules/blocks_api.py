@@ -156,15 +156,31 @@ def dit_forward_modular(model, x, t, context, seq_len, y=None, sp_group=None):
     eng = model._engine
     B, d = len(x), model.dim
     xres, e, e0, ctx, grids, seq_lens = eng.embed(x, t, context, seq_len, 1, 0)
-    xs = xres.view(B, seq_len, d)
-    ev = e.view(B, 1, d)
-    e0v = e0.view(B, 1, 6, d)
+    # the embedding is bf16 in the reference (autocast), and block 0's LayerNorm result is rounded back to
+    # it (`.type_as(x)`, model.py:97): hand block 0 a bf16 tensor (exact: the values are bf16 numbers) so
+    # that attention_block rounds like DiTEngine and the reference do; later blocks get fp32 (model.py:245)
+    xs = xres.view(B, seq_len, d).to(bf16)
+    l1 = e.shape[0] // B                       # 1, or seq_len with per-token timesteps
+    ev = e.view(B, l1, d)
+    e0v = e0.view(B, l1, 6, d)
     ctxv = ctx.view(B, model.text_len, d)
     sp = dutil.get_world_size(sp_group) if sp_group is not None else 1
     if sp > 1:
+        # rows and context are sharded below: BOTH attention forwards of every block must be the
+        # sequence-parallel variants, or the one left local would silently attend within a 1/sp shard
+        from ..distributed.full_sequence_parallel import sp_attn_forward, sp_cross_attn_forward
+        for i, blk in enumerate(model.blocks):
+            for mod, want in ((blk.self_attn, sp_attn_forward), (blk.cross_attn, sp_cross_attn_forward)):
+                if getattr(mod.forward, "__func__", None) is not want:
+                    raise RuntimeError(
+                        f"dit_forward_modular with a sequence-parallel group: blocks[{i}].{type(mod).__name__}."
+                        f"forward is not {want.__name__}; rebind both attention forwards "
+                        "(x2x_gen_unified.py:176-182) or use the engine path (model.sp_group)")
         r = dutil.get_rank(sp_group)
         xs = torch.chunk(xs, sp, dim=1)[r]
         ctxv = torch.chunk(ctxv, sp, dim=1)[r]
+        if l1 > 1:
+            ev, e0v = torch.chunk(ev, sp, dim=1)[r], torch.chunk(e0v, sp, dim=1)[r]
     kwargs = dict(e=e0v, seq_lens=torch.tensor(seq_lens, dtype=torch.long),
                   grid_sizes=torch.tensor(grids, dtype=torch.long), freqs=model.freqs,
                   context=ctxv, context_lens=None)

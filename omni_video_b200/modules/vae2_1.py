@@ -249,9 +249,12 @@ class Wan2_1_VAE:
 # ------------------------------------------------------------------------------------------------
 # Spatial strips across GPUs: rank r of p owns latent rows [h0, h1) of every
 # activation (x 2^k at finer levels).  Per-voxel work is strip-local; a convolution with a spatial
-# extent needs one row of halo from each neighbour at ITS input resolution, exchanged with NCCL
-# point-to-point calls right before the conv; the single-head attention of the middle block gathers
-# the (latent-resolution) rows of all strips.  The reference decodes on one rank only
+# extent needs one row of halo from each neighbour at ITS input resolution.  In strip mode every
+# activation therefore lives in a tensor with one halo slot above and below its rows
+# ([T, 1 + Hl + 1, W, C]; `VAEEngine._pad`): the kernels write the interior through their output
+# strides, the two boundary rows are exchanged in place right before a spatial conv (`halo_fill`),
+# and the conv reads the padded tensor as it is — the activation itself is never copied.  The
+# single-head attention of the middle block gathers the (latent-resolution) rows of all strips.  The reference decodes on one rank only
 # (x2x_gen_unified.py:512-524); this is the multi-GPU layout of BASELINE.json configs[4].
 # ------------------------------------------------------------------------------------------------
 class Strip:
@@ -268,31 +271,42 @@ class Strip:
         return (r * H) // self.p, ((r + 1) * H) // self.p
 
 
-def halo_exchange(x: torch.Tensor, strip: Strip, top: bool, bottom: bool) -> torch.Tensor:
-    """x: this rank's rows [T, Hl, W, C].  Returns x with one halo row from the upper neighbour
-    prepended (if `top`) and one from the lower neighbour appended (if `bottom`); zeros at the
-    image border, which is exactly the convolution's zero padding there."""
+def halo_fill(xp: torch.Tensor, strip: Strip, top: bool, bottom: bool) -> None:
+    """xp: this rank's rows WITH one halo slot above and below, [T, 1 + Hl + 1, W, C].  Fills slot 0 with
+    the upper neighbour's last row (if `top`) and slot Hl+1 with the lower neighbour's first row (if
+    `bottom`); zeros at the image border, which is exactly the convolution's zero padding there.
+    In place: the activation is allocated padded by the kernel that produces it (the conv writes the
+    interior rows through its output strides), so no copy of the activation is made for the halo —
+    only the two boundary rows travel."""
     import torch.distributed as dist
     r, p = strip.r, strip.p
-    t_halo = torch.zeros_like(x[:, :1])
-    b_halo = torch.zeros_like(x[:, :1])
-    ops_ = []
+    ops_, recv_top, recv_bot = [], None, None
     # my first row is the upper neighbour's bottom halo; my last row the lower neighbour's top halo
     if r > 0:
         if bottom:
-            ops_.append(dist.P2POp(dist.isend, x[:, :1].contiguous(), strip.ranks[r - 1], group=strip.group))
+            ops_.append(dist.P2POp(dist.isend, xp[:, 1].contiguous(), strip.ranks[r - 1], group=strip.group))
         if top:
-            ops_.append(dist.P2POp(dist.irecv, t_halo, strip.ranks[r - 1], group=strip.group))
+            recv_top = torch.empty_like(xp[:, 0])
+            ops_.append(dist.P2POp(dist.irecv, recv_top, strip.ranks[r - 1], group=strip.group))
     if r < p - 1:
         if top:
-            ops_.append(dist.P2POp(dist.isend, x[:, -1:].contiguous(), strip.ranks[r + 1], group=strip.group))
+            ops_.append(dist.P2POp(dist.isend, xp[:, -2].contiguous(), strip.ranks[r + 1], group=strip.group))
         if bottom:
-            ops_.append(dist.P2POp(dist.irecv, b_halo, strip.ranks[r + 1], group=strip.group))
+            recv_bot = torch.empty_like(xp[:, 0])
+            ops_.append(dist.P2POp(dist.irecv, recv_bot, strip.ranks[r + 1], group=strip.group))
     if ops_:
         for req in dist.batch_isend_irecv(ops_):
             req.wait()
-    parts = ([t_halo] if top else []) + [x] + ([b_halo] if bottom else [])
-    return torch.cat(parts, dim=1)
+    if top:
+        if recv_top is not None:
+            xp[:, 0].copy_(recv_top)
+        else:
+            xp[:, 0].zero_()
+    if bottom:
+        if recv_bot is not None:
+            xp[:, -1].copy_(recv_bot)
+        else:
+            xp[:, -1].zero_()
 
 
 def gather_rows(x: torch.Tensor, strip: Strip, dim: int, sizes: List[int]) -> torch.Tensor:
@@ -373,19 +387,46 @@ class VAEEngine:
         return self._packed[key]
 
     # -------------------------------------------------------------------------------- blocks
-    def _halo(self, x, pc):
-        """Strip mode: add the halo rows `pc` reads.  Returns (input tensor, row shift of the taps)."""
+    # Activations are [T, pad + H + pad, W, C] with pad = 1 in strip mode (one halo slot above and below
+    # this rank's H rows), pad = 0 on a single GPU; everything below is written once for both.
+    @property
+    def _pad(self) -> int:
+        return 0 if self.strip is None else 1
+
+    def _new_act(self, T, H, W, C):
+        return torch.empty((T, H + 2 * self._pad, W, C), device=self.dev, dtype=bf16)
+
+    def _interior(self, x):
+        return x if self._pad == 0 else x[:, 1:-1]
+
+    def _to_act(self, x):
+        """A dense [T, H, W, C] tensor -> the engine's activation layout."""
+        if self._pad == 0:
+            return x
+        y = self._new_act(x.shape[0], x.shape[1], x.shape[2], x.shape[3])
+        y[:, 1:-1].copy_(x)
+        return y
+
+    def _apply_conv(self, x, pc, out_hw=None, resid=None, want_norm_out=False, **kw):
+        """ovb_conv3d on the activation layout: fills the halo rows `pc` reads (strip mode), lets the conv
+        read the padded tensor as it is (every tap's row offset shifted by the pad) and write the interior
+        rows of a new padded tensor through its output strides."""
+        pad = self._pad
+        T, Hp, W, _ = x.shape
         lo, hi = pc.spatial_rows
-        if self.strip is None or (lo == 0 and hi == 0):
-            return x, 0
-        top, bottom = lo < 0, hi > 0
-        return halo_exchange(x, self.strip, top, bottom), (1 if top else 0)
+        if pad and (lo != 0 or hi != 0):
+            halo_fill(x, self.strip, lo < 0, hi > 0)
+        H, Wo = out_hw if out_hw is not None else (Hp - 2 * pad, W)
+        co = pc.cout
+        out = self._new_act(T, H, Wo, co)
+        if want_norm_out:
+            kw["norm_out"] = self._new_act(T, H, Wo, co)
+        vae_ops.conv3d(x, pc, (T, H, Wo), out=out, out_strides=((H + 2 * pad) * Wo * co, Wo * co, co),
+                       out_base=pad * Wo * co, resid=resid, dh_shift=pad, **kw)
+        return (out, kw["norm_out"]) if want_norm_out else out
 
     def _causal_conv(self, x, name, resid=None, **kw):
-        T, H, W, _ = x.shape
-        pc = self._conv(name)
-        xin, shift = self._halo(x, pc)
-        return vae_ops.conv3d(xin, pc, (T, H, W), resid=resid, dh_shift=shift, **kw)
+        return self._apply_conv(x, self._conv(name), resid=resid, **kw)
 
     def _residual_block(self, x, p, x_norm=None, next_gamma=None, raw_needed=True):
         """reference vae2_1.py:185-219: x + conv(act(norm(conv(act(norm(x)))))) (+ 1x1x1 shortcut).
@@ -416,14 +457,18 @@ class VAEEngine:
         if (next_gamma is not None and fuse and vae_ops.can_fuse_norm(pc2) and next_gamma.numel() == pc2.cout
                 and (dual_ok or not raw_needed)):
             if raw_needed:
-                yn = torch.empty((x.shape[0], x.shape[1], x.shape[2], pc2.cout), device=x.device, dtype=bf16)
-                y = self._causal_conv(b, p + "residual.6", resid=h, norm_gamma=next_gamma, norm_out=yn)
-                return y, yn
+                return self._causal_conv(b, p + "residual.6", resid=h, norm_gamma=next_gamma, want_norm_out=True)
             return None, self._causal_conv(b, p + "residual.6", resid=h, norm_gamma=next_gamma)
         y = self._causal_conv(b, p + "residual.6", resid=h)
         return y, None
 
     def _attention_block(self, x, p):
+        if self._pad:
+            # latent resolution, 3 % of the FLOPs: on a dense copy of this rank's rows
+            return self._to_act(self._attention_dense(self._interior(x).contiguous(), p))
+        return self._attention_dense(x, p)
+
+    def _attention_dense(self, x, p):
         T, H, W, Cc = x.shape
         hw = H * W
         if hw % 8 != 0 and self.strip is None:
@@ -467,15 +512,18 @@ class VAEEngine:
         return y.view(T, H, W, Cc)
 
     def _upsample(self, x, p, three_d: bool):
-        T, H, W, Cc = x.shape
+        pad = self._pad
+        T, Hp, W, Cc = x.shape
+        H = Hp - 2 * pad
         sd = self._params()
         if three_d and T > 1:
-            # time_conv over frames 1.. (zero left context), channel halves -> consecutive frames
+            # time_conv over frames 1.. (zero left context), channel halves -> consecutive frames.  No
+            # spatial extent: the halo slots are processed like rows (and refilled before the next use)
             pc = self._conv(p + "time_conv")
-            y = torch.empty((1 + 2 * (T - 1), H, W, Cc), device=x.device, dtype=bf16)
+            y = torch.empty((1 + 2 * (T - 1), Hp, W, Cc), device=x.device, dtype=bf16)
             y[0].copy_(x[0])
-            fr = H * W * Cc
-            vae_ops.conv3d(x[1:], pc, (T - 1, H, W), out=y, out_strides=(2 * fr, W * Cc, Cc), out_base=fr,
+            fr = Hp * W * Cc
+            vae_ops.conv3d(x[1:], pc, (T - 1, Hp, W), out=y, out_strides=(2 * fr, W * Cc, Cc), out_base=fr,
                            n_group=Cc, group_stride=fr)
             x, T = y, y.shape[0]
         key = p + "resample.1#phases"
@@ -484,31 +532,35 @@ class VAEEngine:
                                                              sd[p + "resample.1.bias"])
         phases = self._packed[key]
         Co = Cc // 2
-        out = torch.empty((T, 2 * H, 2 * W, Co), device=x.device, dtype=bf16)
-        # strip mode: one halo exchange (both neighbours) serves the four phases
-        xin, shift = (x, 0) if self.strip is None else (halo_exchange(x, self.strip, True, True), 1)
+        out = self._new_act(T, 2 * H, 2 * W, Co)
+        if pad:  # one halo fill (both neighbours) serves the four phases
+            halo_fill(x, self.strip, True, True)
+        row = 2 * W * Co                        # one output row
         for (a, b), pc in phases.items():
-            vae_ops.conv3d(xin, pc, (T, H, W), out=out, out_strides=(4 * H * W * Co, 4 * W * Co, 2 * Co),
-                           out_base=(a * 2 * W + b) * Co, dh_shift=shift)
+            vae_ops.conv3d(x, pc, (T, H, W), out=out, out_strides=((2 * H + 2 * pad) * row, 2 * row, 2 * Co),
+                           out_base=(pad + a) * row + b * Co, dh_shift=pad)
         return out
 
     def _downsample(self, x, p, three_d: bool):
-        T, H, W, Cc = x.shape
+        pad = self._pad
+        T, Hp, W, Cc = x.shape
+        H = Hp - 2 * pad
         Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1                     # ZeroPad2d(0,1,0,1) + k3 s2
         pc = self._conv(p + "resample.1", stride=(1, 2, 2), spatial_pad=(0, 0))
-        if self.strip is not None:
+        if pad:
             assert H % 2 == 0, "strip heights must be even at every stride-2 level"
-            Ho = H // 2
-            x = halo_exchange(x, self.strip, False, True)    # rows 2h, 2h+1, 2h+2: one row from below
-        x = vae_ops.conv3d(x, pc, (T, Ho, Wo))
+            Ho = H // 2                          # rows 2h, 2h+1, 2h+2: the last one may be the lower halo
+        x = self._apply_conv(x, pc, out_hw=(Ho, Wo))
         if three_d and T > 1:
-            # out[0] = x[0]; out[j] = time_conv(x[2j-2], x[2j-1], x[2j])  (stride 2, no padding)
+            # out[0] = x[0]; out[j] = time_conv(x[2j-2], x[2j-1], x[2j])  (stride 2, no padding); no spatial
+            # extent: halo slots are processed like rows
             To = 1 + (T - 1) // 2
             pt = self._conv(p + "time_conv", causal_pad=0, stride=(2, 1, 1))
-            y = torch.empty((To, Ho, Wo, Cc), device=x.device, dtype=bf16)
+            Hq = Ho + 2 * pad
+            y = torch.empty((To, Hq, Wo, Cc), device=x.device, dtype=bf16)
             y[0].copy_(x[0])
-            fr = Ho * Wo * Cc
-            vae_ops.conv3d(x, pt, (To - 1, Ho, Wo), out=y, out_strides=(fr, Wo * Cc, Cc), out_base=fr)
+            fr = Hq * Wo * Cc
+            vae_ops.conv3d(x, pt, (To - 1, Hq, Wo), out=y, out_strides=(fr, Wo * Cc, Cc), out_base=fr)
             x = y
         return x
 
@@ -559,20 +611,23 @@ class VAEEngine:
                 self._lat_H = x.shape[1]
                 h0, h1 = self.strip.rows(self._lat_H)
                 assert h1 > h0, "more strips than latent rows"
-                x = x[:, h0:h1].contiguous()
-            T, H, W, _ = x.shape
-            x = vae_ops.conv3d(x, self._conv("conv2"), (T, H, W))                # 1x1x1 (:552)
+                x = x[:, h0:h1]
+            x = self._to_act(x)
+            x = self._causal_conv(x, "conv2")                                    # 1x1x1 (:552)
             x = self._causal_conv(x, "decoder.conv1")
             x = self._stack(x, "decoder.middle.", up=True)
             head_gamma = self._gamma("decoder.head.0.gamma")
             x = self._stack(x, "decoder.upsamples.", up=True, tail_gamma=head_gamma)
             if not self._tail_fused:
                 vae_ops.rmsnorm_silu(x, head_gamma, out=x)
-            T, H, W, _ = x.shape
+            pad = self._pad
+            T, Hp, W, _ = x.shape
+            H = Hp - 2 * pad
             out = torch.empty((3, T, H, W), device=self.dev, dtype=f32)
             pc_head = self._conv("decoder.head.2")
-            x, hshift = self._halo(x, pc_head)
-            vae_ops.conv3d(x, pc_head, (T, H, W), out=out, out_strides=(H * W, W, 1), dh_shift=hshift,
+            if pad:
+                halo_fill(x, self.strip, True, True)
+            vae_ops.conv3d(x, pc_head, (T, H, W), out=out, out_strides=(H * W, W, 1), dh_shift=pad,
                            out_mode=CONV_OUT_F32_PLANAR_CLAMP if clamp else vae_ops.CONV_OUT_F32_PLANAR,
                            plane_stride=T * H * W)
             if self.strip is not None:  # every rank ends up with the whole clip
@@ -596,7 +651,7 @@ class VAEEngine:
                 h0, h1 = self.strip.rows(self._lat_H)
                 assert h1 > h0, "more strips than latent rows"
                 v = v[:, :, 8 * h0:8 * h1].contiguous()
-            x = vae_ops.planar_to_cl(v, self._ones[3], self._zeros[3], 16)
+            x = self._to_act(vae_ops.planar_to_cl(v, self._ones[3], self._zeros[3], 16))
             x = self._causal_conv(x, "encoder.conv1")
             x = self._stack(x, "encoder.downsamples.", up=False)
             head_gamma = self._gamma("encoder.head.0.gamma")
@@ -604,11 +659,11 @@ class VAEEngine:
             if not self._tail_fused:
                 vae_ops.rmsnorm_silu(x, head_gamma, out=x)
             x = self._causal_conv(x, "encoder.head.2")                            # [T', h, w, 32]
-            T, H, W, _ = x.shape
-            x = vae_ops.conv3d(x, self._conv("conv1"), (T, H, W))                # 1x1x1 (:534)
+            x = self._causal_conv(x, "conv1")                                     # 1x1x1 (:534)
             z = self.mean.numel()
             inv = 1.0 / self.std
-            mu = vae_ops.cl_to_planar(x, inv, -self.mean * inv, z)                # (mu - mean)/std (:535-539)
+            x = self._interior(x)
+            mu = vae_ops.cl_to_planar(x if x.is_contiguous() else x.contiguous(), inv, -self.mean * inv, z)  # (:535-539)
             if self.strip is not None:
                 sizes = [self.strip.rows(self._lat_H, r)[1] - self.strip.rows(self._lat_H, r)[0]
                          for r in range(self.strip.p)]

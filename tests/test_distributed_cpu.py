@@ -114,19 +114,24 @@ def _strip_worker(rank, world, port, results):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from omni_video_b200.modules.vae2_1 import Strip, gather_rows, halo_exchange
+        from omni_video_b200.modules.vae2_1 import Strip, gather_rows, halo_fill
         strip = Strip(dist.new_group(list(range(world))))
         H = 7                                        # uneven strips: 3 + 4 rows
         full = torch.arange(2 * H * 3 * 4, dtype=torch.float32).view(2, H, 3, 4)   # [T, H, W, C]
         h0, h1 = strip.rows(H)
         assert (h0, h1) == ((0, 3) if rank == 0 else (3, 7))
         mine = full[:, h0:h1].contiguous()
-        ext = halo_exchange(mine, strip, True, True)
+        # activations carry one halo slot above and below their rows; halo_fill fills them in place
+        ext = torch.full((2, (h1 - h0) + 2, 3, 4), -7.0)
+        ext[:, 1:-1] = mine
+        halo_fill(ext, strip, True, True)
         want = torch.cat([full[:, h0 - 1:h0] if h0 > 0 else torch.zeros_like(full[:, :1]), mine,
                           full[:, h1:h1 + 1] if h1 < H else torch.zeros_like(full[:, :1])], dim=1)
         assert torch.equal(ext, want)
-        only_bottom = halo_exchange(mine, strip, False, True)
-        assert torch.equal(only_bottom, want[:, 1:])
+        only_bottom = torch.full((2, (h1 - h0) + 2, 3, 4), -7.0)
+        only_bottom[:, 1:-1] = mine
+        halo_fill(only_bottom, strip, False, True)
+        assert torch.equal(only_bottom[:, 1:], want[:, 1:]) and bool((only_bottom[:, 0] == -7.0).all())
         sizes = [strip.rows(H, r)[1] - strip.rows(H, r)[0] for r in range(world)]
         assert torch.equal(gather_rows(mine, strip, 1, sizes), full)
         results[rank] = "ok"

@@ -135,7 +135,7 @@ def test_module_granular_hooks_match_engine():
     cfg, sd, xs, t, ctx, seq_len = dit_case(meta)
     model = _build(cfg, sd)
     out_engine = model([x.cuda() for x in xs], t=t.cuda(), context=[c.cuda() for c in ctx], seq_len=seq_len)[0]
-    from omni_video_b200.modules.reference_style import forward_module_granular
+    from omni_video_b200.modules.blocks_api import dit_forward_modular as forward_module_granular
     out_mod = forward_module_granular(model, [x.cuda() for x in xs], t.cuda(), [c.cuda() for c in ctx], seq_len)[0]
     assert O.rel_l2(out_mod.cpu(), out_engine.cpu()) < 5e-3
 
