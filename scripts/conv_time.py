@@ -39,11 +39,19 @@ def run(cin, cout, T, H, W, tag):
         ts.append(e0.elapsed_time(e1))
     ms = sorted(ts)[2]
     fl = 2.0 * T * H * W * cout * 27 * cin
-    print(f"{tag}: conv {cin}->{cout} [{T},{H},{W}]: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s", flush=True)
+    kc = 64 if cin % 64 == 0 else (32 if cin % 32 == 0 else 16)
+    n_mma = 27 * cin // 16 * (T * H * W / 256.0) / 74.0          # pair MMAs per CTA pair
+    print(f"{tag}: conv {cin}->{cout} [{T},{H},{W}]: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s  "
+          f"(KC {kc}: ~{ms * 1e-3 * 1.9e9 / n_mma:.0f} cycles per M=256,N={cout},K=16 MMA at 1.9 GHz; floor {cout // 2})", flush=True)
 
 
 if __name__ == "__main__":
     tag = f"brick={'0' if os.environ.get('OVB_CONV_NO_BRICK') else '1'} box_l2={os.environ.get('OVB_CONV_BOX_L2', 'auto')}"
+    if "--sweep" in sys.argv:
+        # cycles per MMA vs channel-chunk width (swizzle mode) and N: Cin 32/96 -> 64-byte rows, 64/128 -> 128-byte
+        for cin, cout in [(32, 96), (64, 96), (96, 96), (128, 96), (64, 64), (128, 128), (96, 192), (192, 96)]:
+            run(cin, cout, 9, 480, 832, tag)
+        sys.exit(0)
     run(96, 96, 21, 480, 832, tag)
     if "--all" in sys.argv:
         run(192, 192, 21, 240, 416, tag)
