@@ -55,6 +55,39 @@ def test_denoise_loop_two_experts_matches_stepwise_restatement():
     assert O.rel_l2(got.float().cpu(), want) <= 2e-3
 
 
+def test_denoise_loop_vs_cpu_oracle_end_to_end():
+    """The WHOLE loop against the CPU oracle, nothing shared with the GPU path: every forward of the
+    restatement is `oracle.dit.dit_forward` (bf16-emulating, on bf16-rounded weights, fp32 CPU), guidance and
+    the UniPC update are `oracle.unipc`.  Four steps of a two-expert schedule on the tiny DiT; the latent after
+    the last step must agree within the north-star per-step tolerance, although errors compound over steps."""
+    from omni_video_b200.sampling import DenoiseLoop
+    cfg = dict(synth.TINY_DIT)
+    sd_hi, sd_lo = synth.dit_state_dict(cfg, seed=11), synth.dit_state_dict(cfg, seed=12)
+    hi, lo = _expert(11), _expert(12)
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(16, 2, 8, 8, generator=g).to(bf16).float()
+    ctx_c = torch.randn(12, 64, generator=g).to(bf16)
+    ctx_u = torch.randn(5, 64, generator=g).to(bf16)
+    L, steps, shift, gs, boundary = 2 * 4 * 4, 4, 5.0, 3.0, 0.9
+
+    o = UniPCOracle()
+    o.set_timesteps(steps, shift)
+    want = noise.clone()
+    for t in o.timesteps:
+        sd = synth.round_bf16(sd_hi if t.item() >= boundary * 1000 else sd_lo)
+        xin = [want.to(bf16).float()]                     # the loop keeps bf16 latents (x2x_gen_unified.py:382-391)
+        c = O.dit_forward(sd, cfg, xin, t.reshape(1), [ctx_c.float()], L, emulate_bf16=True)[0]
+        u = O.dit_forward(sd, cfg, xin, t.reshape(1), [ctx_u.float()], L, emulate_bf16=True)[0]
+        want = o.step(u + gs * (c - u), want.unsqueeze(0)).squeeze(0)
+
+    loop = DenoiseLoop(hi, lo, boundary=boundary)
+    got = loop.sample(noise.cuda(), dict(context=[ctx_c.cuda()], seq_len=L), dict(context=[ctx_u.cuda()], seq_len=L),
+                      sampling_steps=steps, shift=shift, guide_scale=gs)[0]
+    err = O.rel_l2(got.float().cpu(), want)
+    print(f"denoise loop, {steps} steps, two experts: rel-L2 vs the CPU oracle loop {err:.3e}")
+    assert bool(torch.isfinite(got).all()) and err <= 1e-2
+
+
 def test_denoise_loop_unified_model_batched_equals_unbatched_and_keeps_rng_stream():
     from omni_video_b200.sampling import DenoiseLoop
     from tests.test_gpu_unified import build, to_cuda
