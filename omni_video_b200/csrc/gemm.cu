@@ -36,8 +36,15 @@ constexpr int kStages = 6;
 constexpr int kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kBBytes = (kBN / 2) * kBK * 2;  // 16 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kGemmThreads = 256;
-constexpr int kStagingBytes = 4 * 32 * 32 * 4;  // one 32x32 fp32 transpose buffer per epilogue warp
+constexpr int kGemmThreads = 256;   // gemm_resid_tma_kernel: 4 service warps + 4 epilogue warps
+// gemm_bf16_kernel runs EIGHT epilogue warps, two per scheduler and TMEM lane quadrant (warps w and
+// w + 4 may both access lanes 32 (w % 4) .. + 31), each taking every other 32-column chunk.  One warp
+// per scheduler executes the epilogue at 5-7 cycles per instruction (dependent chains, MUFU latency,
+// nobody to switch to): with the GELU — or at K = 1536 any — epilogue that outlasted the main loop
+// (FFN1 [65520, 8960, 1536]: 1.53 ms with GELU against 1.14 ms without).
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreadsEpi8 = 128 + 32 * kEpiWarps;
+constexpr int kStagingBytes = kEpiWarps * 32 * 32 * 4;  // one 32x32 fp32 transpose buffer per epilogue warp
 constexpr int kGemmSmem = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct GemmParams {
@@ -58,7 +65,7 @@ struct GemmParams {
 };
 
 template <int kEpi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreadsEpi8, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -91,7 +98,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(&tempty_bar[a], 2 * kEpiWarps);  // epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -168,8 +175,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (both CTAs)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    float* stg = staging + quad * (32 * 32);
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int chunk0 = (warp - 4) >> 2;  // this warp's first 32-column chunk; it takes every other one
+    float* stg = staging + (warp - 4) * (32 * 32);
     const uint32_t stg_addr = smem_u32(stg);
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const int rr_off = lane >> 3;  // row inside a group of 4 in the read phase
@@ -185,13 +193,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // accumulator is ready so its latency hides behind the main loop
       uint2 bw_next = make_uint2(0u, 0u);
       {
-        const int col = n_tile * kBN + cj * 4;
+        const int col = n_tile * kBN + chunk0 * 32 + cj * 4;
         if (p.bias != nullptr && col < p.N) bw_next = *reinterpret_cast<const uint2*>(p.bias + col);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
+      for (int c = chunk0; c < kBN / 32; c += 2) {
         const int col0 = n_tile * kBN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
@@ -199,8 +207,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col = col0 + cj * 4;
         const bool col_ok = col < p.N;
         const uint2 bw = bw_next;
-        if (p.bias != nullptr && col + 32 < p.N && c + 1 < kBN / 32)
-          bw_next = *reinterpret_cast<const uint2*>(p.bias + col + 32);
+        if (p.bias != nullptr && col + 64 < p.N && c + 2 < kBN / 32)
+          bw_next = *reinterpret_cast<const uint2*>(p.bias + col + 64);
         // operands of the residual epilogues: all 8 row groups are requested up front, before
         // any store of this chunk is issued (a store may alias them as far as the compiler knows)
         float4 xr[8], gt[8];
@@ -281,8 +289,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   make_float4(v[0], v[1], v[2], v[3]);
             } else {
               if constexpr (kEpi == OVB_EPI_GELU_BF16) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
+                // the Linear's bf16 result (model.py:211 under autocast), then GELU in fp32, two values
+                // per instruction: at K = 1536 this epilogue used to outlast the main loop (FFN1 ran at
+                // 1176 TF/s against 1561 with the plain epilogue)
+                uint32_t p01 = pack_bf16x2(v[0], v[1]), p23 = pack_bf16x2(v[2], v[3]);
+                const uint64_t g01 = gelu_tanh_x2(pack_f32x2(__uint_as_float(p01 << 16), __uint_as_float(p01 & 0xffff0000u)));
+                const uint64_t g23 = gelu_tanh_x2(pack_f32x2(__uint_as_float(p23 << 16), __uint_as_float(p23 & 0xffff0000u)));
+                unpack_f32x2(g01, v[0], v[1]);
+                unpack_f32x2(g23, v[2], v[3]);
               } else if constexpr (kEpi == OVB_EPI_RESID_BF16) {
                 const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].x));
                 const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].y));
@@ -686,12 +700,12 @@ extern "C" int ovb_gemm_bf16(const ovb_gemm_args* a, void* stream) {
     return OVB_OK;
   }
   switch (a->epilogue) {
-    case OVB_EPI_BF16: gemm_bf16_kernel<OVB_EPI_BF16><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
-    case OVB_EPI_GELU_BF16: gemm_bf16_kernel<OVB_EPI_GELU_BF16><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
-    case OVB_EPI_RESID_F32: gemm_bf16_kernel<OVB_EPI_RESID_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
-    case OVB_EPI_GATE_RESID_F32: gemm_bf16_kernel<OVB_EPI_GATE_RESID_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
-    case OVB_EPI_F32: gemm_bf16_kernel<OVB_EPI_F32><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
-    default: gemm_bf16_kernel<OVB_EPI_RESID_BF16><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_BF16: gemm_bf16_kernel<OVB_EPI_BF16><<<grid, kGemmThreadsEpi8, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_GELU_BF16: gemm_bf16_kernel<OVB_EPI_GELU_BF16><<<grid, kGemmThreadsEpi8, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_RESID_F32: gemm_bf16_kernel<OVB_EPI_RESID_F32><<<grid, kGemmThreadsEpi8, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_GATE_RESID_F32: gemm_bf16_kernel<OVB_EPI_GATE_RESID_F32><<<grid, kGemmThreadsEpi8, kGemmSmem, st>>>(tmA, tmB, p); break;
+    case OVB_EPI_F32: gemm_bf16_kernel<OVB_EPI_F32><<<grid, kGemmThreadsEpi8, kGemmSmem, st>>>(tmA, tmB, p); break;
+    default: gemm_bf16_kernel<OVB_EPI_RESID_BF16><<<grid, kGemmThreadsEpi8, kGemmSmem, st>>>(tmA, tmB, p); break;
   }
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
