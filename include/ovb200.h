@@ -31,7 +31,7 @@ extern "C" {
 #define OVB_ERR_CUDA (-2)
 #define OVB_ERR_UNSUPPORTED_ARCH (-3)
 
-#define OVB_ABI_VERSION 2
+#define OVB_ABI_VERSION 3
 
 /* ---- library ---------------------------------------------------------------------------- */
 int ovb_abi_version(void);
@@ -299,6 +299,8 @@ int ovb_lincomb(const ovb_lincomb_args* args, void* stream);
  *   (n_group = 0: no grouping).  Doubled os_h/os_w + a phase offset in out_base writes one phase of a
  *   2x nearest-upsampled image (Upsample + Conv2d, :75-84, as four 2x2 convs); n_group = C with
  *   group_stride = os_t interleaves time_conv's two channel halves as consecutive frames (:133-136).
+ *   n_group a multiple of 16, or (w_rows % 32 == 0, no resid, no norm) a multiple of 4 below 16: per-group
+ *   planes such as [group][T][H][W][4], the input of ovb_tap_sum; strides then need 4-element alignment.
  * OVB_CONV_OUT_F32_PLANAR(_CLAMP): fp32 out[n*plane_stride + out_base + t*os_t + h*os_h + w*os_w],
  *   optionally clamped to [-1,1] (Wan2_1_VAE.decode, :660).
  */
@@ -339,6 +341,28 @@ typedef struct ovb_conv3d_args {
 } ovb_conv3d_args;
 
 int ovb_conv3d(const ovb_conv3d_args* args, void* stream);
+
+/* Sum of per-tap partial products: the second half of a convolution with very few output channels
+ * (the decoder head, CausalConv3d 96 -> 3, vae2_1.py:164-165 / :469).  As an implicit GEMM such a conv pays a
+ * full A-operand fetch per MMA for 3 useful columns; instead ovb_conv3d computes, as ONE 1x1x1 conv with
+ * n_taps*4 output columns and n_group = 4, the planes  y[k][t][h][w][c] = sum_ci W[c][ci][tap k] * x[t][h][w][ci]
+ * (bf16), and this kernel shifts and adds them:
+ *   out[c][t][h][w] = bias[c] + sum_k y[k][t + dt_k][h + dh_k][w + dw_k][c]      (fp32, planar; clamp to [-1, 1])
+ * with terms outside y's extents equal to zero (causal and spatial zero padding).  HBM-bound:
+ * 8 B x n_taps read + 4 B x C written per output voxel.  y: bf16 [n_taps][Ty][Hy][Wy][4], 8-byte aligned. */
+typedef struct {
+  const void* y;
+  int32_t n_taps;
+  const int8_t *tap_dt, *tap_dh, *tap_dw;
+  int32_t Ty, Hy, Wy;
+  const float* bias; /* [C] or NULL */
+  float* out;        /* fp32 [C][To][Ho][Wo] */
+  int32_t C;         /* 1..4 */
+  int32_t To, Ho, Wo;
+  int32_t clamp;
+} ovb_tap_sum_args;
+
+int ovb_tap_sum(const ovb_tap_sum_args* args, void* stream);
 
 /* RMS_norm over channels (+ optional SiLU) on channels-last voxels (vae2_1.py:38-53, :194-196):
  * out[v, c] = act( x[v, c] / max(||x[v, :]||_2, 1e-12) * sqrt(C) * gamma[c] ).  HBM-bound: 4 B/elem. */

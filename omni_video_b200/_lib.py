@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OVB_LIB_PATH") or os.path.join(_HERE, "libovb200.so")
 
 OVB_OK = 0
-ABI_VERSION = 2   # include/ovb200.h OVB_ABI_VERSION
+ABI_VERSION = 3   # include/ovb200.h OVB_ABI_VERSION
 
 # epilogues / modes (mirror include/ovb200.h)
 EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_GATE_RESID_F32, EPI_F32, EPI_RESID_BF16 = range(6)
@@ -100,6 +100,17 @@ class ConvArgs(C.Structure):
     ]
 
 
+class TapSumArgs(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p), ("n_taps", C.c_int32),
+        ("tap_dt", C.POINTER(C.c_int8)), ("tap_dh", C.POINTER(C.c_int8)), ("tap_dw", C.POINTER(C.c_int8)),
+        ("Ty", C.c_int32), ("Hy", C.c_int32), ("Wy", C.c_int32),
+        ("bias", C.c_void_p), ("out", C.c_void_p),
+        ("C", C.c_int32), ("To", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("clamp", C.c_int32),
+    ]
+
+
 class LinCombArgs(C.Structure):
     _fields_ = [("x", C.c_void_p * 5), ("c", C.c_float * 5), ("is_bf16", C.c_int32 * 5),
                 ("n_terms", C.c_int32), ("round_mask", C.c_int32), ("out", C.c_void_p),
@@ -141,6 +152,7 @@ _SIGNATURES = {
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ovb_lincomb": (C.c_int, [C.POINTER(LinCombArgs), C.c_void_p]),
     "ovb_conv3d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "ovb_tap_sum": (C.c_int, [C.POINTER(TapSumArgs), C.c_void_p]),
     "ovb_rmsnorm_silu_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_int32, C.c_void_p]),
     "ovb_planar_to_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -312,7 +312,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t stg_addr = smem_u32(staging + quad * (32 * 32));
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const int rr_off = lane >> 3, cj = lane & 7;
-    const bool transposed = p.out_mode == OVB_CONV_OUT_BF16 && (p.BN & 31) == 0;
+    const bool planes = p.out_mode == OVB_CONV_OUT_BF16 && p.n_group < 16;  // narrow channel groups
+    const bool transposed = p.out_mode == OVB_CONV_OUT_BF16 && (p.BN & 31) == 0 && !planes;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -525,6 +526,53 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+      } else if (planes) {
+        // Per-group planes such as [group][T][H][W][4] (ovb_tap_sum's input): voxels are contiguous inside a
+        // plane, so the accumulator's own mapping (lane = voxel) already coalesces — a warp instruction
+        // writes 8 bytes x 32 consecutive voxels of one plane; no transpose.  The epilogue is all there is to
+        // such a conv (K is one tap), so its instruction count is what matters: the plane pointer advances
+        // incrementally, the bias test is hoisted out of the loops.
+        const int hl = r >> p.bw_log2, wl = r & (bw - 1);
+        const int h = ht * p.bh + hl, w = (wt << p.bw_log2) + wl;
+        const bool ok = real && h < p.Ho && w < p.Wo;
+        const int n_first = nt * p.BN;
+        const int g0 = n_first / p.n_group;
+        int inner = n_first - g0 * p.n_group;  // column inside its group
+        __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_base + t * p.os_t + h * p.os_h +
+                            w * p.os_w + g0 * p.group_stride + inner;
+        const long long wrap = p.group_stride - (p.n_group - 4);
+        const bool has_bias = p.bias != nullptr;
+        const int n_chunks = p.BN / 32;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          const int n0 = n_first + c * 32;
+          if (n0 >= p.Cout) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + c * 32, v);
+          tmem_wait_ld();
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.Cout) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + n0 + j));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {  // n_group % 4 == 0: four columns never straddle two groups
+            if (ok && n0 + j < p.Cout) {
+              uint2 o;
+              o.x = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+              o.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              *reinterpret_cast<uint2*>(pp) = o;
+            }
+            inner += 4;
+            if (inner == p.n_group) {
+              inner = 0;
+              pp += wrap;
+            } else {
+              pp += 4;
+            }
+          }
+          __syncwarp();
+        }
       } else {
         const int hl = r >> p.bw_log2, wl = r & (bw - 1);
         const int h = ht * p.bh + hl, w = (wt << p.bw_log2) + wl;
@@ -629,13 +677,20 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
   OVB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w) |
                  reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->resid)) % 16 == 0,
                 "ovb_conv3d: pointers must be 16-byte aligned");
+  // Channel groups narrower than 16 (down to 4 channels = one 8-byte store per voxel and group) turn
+  // the output into per-group planes, e.g. [group][T][H][W][4]: the per-tap partial sums ovb_tap_sum consumes.
+  const bool narrow = a->out_mode == OVB_CONV_OUT_BF16 && a->n_group > 0 && a->n_group < 16;
   if (a->out_mode == OVB_CONV_OUT_BF16) {
-    OVB_CHECK_ARG(a->Cout % 16 == 0, "ovb_conv3d: bf16 output needs Cout %% 16 == 0 (got %d)", a->Cout);
-    OVB_CHECK_ARG(a->os_t % 8 == 0 && a->os_h % 8 == 0 && a->os_w % 8 == 0 && a->out_base % 8 == 0 &&
-                      a->group_stride % 8 == 0,
-                  "ovb_conv3d: bf16 output strides must be multiples of 8 elements");
-    OVB_CHECK_ARG(a->n_group == 0 || (a->n_group % 16 == 0 && a->Cout % a->n_group == 0),
-                  "ovb_conv3d: n_group=%d must be a multiple of 16 dividing Cout", a->n_group);
+    const int al = narrow ? 4 : 8, cal = narrow ? 4 : 16;
+    OVB_CHECK_ARG(a->Cout % cal == 0, "ovb_conv3d: bf16 output needs Cout %% %d == 0 (got %d)", cal, a->Cout);
+    OVB_CHECK_ARG(a->os_t % al == 0 && a->os_h % al == 0 && a->os_w % al == 0 && a->out_base % al == 0 &&
+                      a->group_stride % al == 0,
+                  "ovb_conv3d: bf16 output strides must be multiples of %d elements", al);
+    OVB_CHECK_ARG(a->n_group == 0 || (a->n_group % cal == 0 && a->Cout % a->n_group == 0),
+                  "ovb_conv3d: n_group=%d must be a multiple of 16 (or of 4, below 16) dividing Cout", a->n_group);
+    OVB_CHECK_ARG(!narrow || (a->resid == nullptr && a->norm_gamma == nullptr && a->w_rows % 32 == 0 &&
+                              a->w_rows <= 256),
+                  "ovb_conv3d: channel groups below 16 need w_rows %% 32 == 0, w_rows <= 256, no resid, no norm");
   } else {
     OVB_CHECK_ARG(a->resid == nullptr && a->n_group == 0,
                   "ovb_conv3d: planar fp32 output supports neither resid nor channel groups");
@@ -723,11 +778,12 @@ extern "C" int ovb_conv3d(const ovb_conv3d_args* a, void* stream) {
   // ---- N tile
   p.Cout = a->Cout;
   {
-    const int g = a->n_group > 0 ? a->n_group : a->w_rows;
+    const int g = a->n_group >= 16 ? a->n_group : a->w_rows;
     int bn = 0;
     for (int c = 256; c >= 16; c -= 16)
       if (g % c == 0) { bn = c; break; }
     if (a->n_group == 0 && bn < 64 && a->w_rows > 256) bn = 256;  // awkward Cout: partial last tile
+    if (narrow) bn = a->w_rows;  // one N tile, a multiple of 32 (the planes epilogue reads 32-column chunks)
     p.BN = bn;
     p.n_nt = (a->w_rows + bn - 1) / bn;
   }

@@ -198,6 +198,56 @@ __global__ void video_to_uint8_kernel(const float* __restrict__ x, uint8_t* __re
   }
 }
 
+// Sum of per-tap partial products (the second half of a convolution with very few output channels, see
+// ovb_tap_sum in ovb200.h):  out[c][t][h][w] = bias[c] + sum_k y[k][t + dt_k][h + dh_k][w + dw_k][c],
+// y bf16 [n_taps][Ty][Hy][Wy][4], terms outside y's extents are zero (causal / spatial zero padding).
+// One thread per output voxel, consecutive lanes = consecutive w: every tap is one 8-byte load per lane and
+// 256 contiguous bytes per warp; every y element is read exactly once (8 B x n_taps per voxel in, 4 B x C out).
+struct TapSumParams {
+  const uint2* y;
+  const float* bias;
+  float* out;
+  int n_taps, Ty, Hy, Wy, C, To, Ho, Wo, clamp;
+  signed char dt[27], dh[27], dw[27];
+};
+
+__global__ void __launch_bounds__(256) tap_sum_kernel(const __grid_constant__ TapSumParams p) {
+  const long long n = static_cast<long long>(p.To) * p.Ho * p.Wo;
+  const long long plane = static_cast<long long>(p.Ty) * p.Hy * p.Wy;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(i % p.Wo);
+    const long long r = i / p.Wo;
+    const int h = static_cast<int>(r % p.Ho);
+    const int t = static_cast<int>(r / p.Ho);
+    uint2 v[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      v[k] = make_uint2(0u, 0u);
+      if (k < p.n_taps) {
+        const int tt = t + p.dt[k], hh = h + p.dh[k], ww = w + p.dw[k];
+        if (tt >= 0 && tt < p.Ty && hh >= 0 && hh < p.Hy && ww >= 0 && ww < p.Wy)
+          v[k] = __ldcs(p.y + k * plane + (static_cast<long long>(tt) * p.Hy + hh) * p.Wy + ww);
+      }
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {  // fixed order: deterministic
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[k].x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[k].y));
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < p.C) {
+        float o = acc[c] + (p.bias != nullptr ? p.bias[c] : 0.f);
+        if (p.clamp) o = fminf(fmaxf(o, -1.0f), 1.0f);
+        p.out[c * n + i] = o;
+      }
+    }
+  }
+}
+
 }  // namespace ovb
 
 extern "C" int ovb_rmsnorm_silu_cl(const void* x, const float* gamma, void* out, int64_t n_vox,
@@ -270,6 +320,37 @@ extern "C" int ovb_softmax_rows(const float* S, int64_t lds, void* P, int64_t ld
   OVB_CHECK_ARG(S && P && rows > 0 && cols > 0 && lds >= cols && ldp >= cols, "ovb_softmax_rows: bad arguments");
   softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, cols, scale * 1.4426950408889634f);
+  OVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return OVB_OK;
+}
+
+extern "C" int ovb_tap_sum(const ovb_tap_sum_args* a, void* stream) {
+  using namespace ovb;
+  OVB_CHECK_ARG(a != nullptr && a->y && a->out && a->tap_dt && a->tap_dh && a->tap_dw, "ovb_tap_sum: null pointer");
+  OVB_CHECK_ARG(a->n_taps >= 1 && a->n_taps <= 27, "ovb_tap_sum: n_taps=%d outside [1,27]", a->n_taps);
+  OVB_CHECK_ARG(a->C >= 1 && a->C <= 4, "ovb_tap_sum: C=%d outside [1,4]", a->C);
+  OVB_CHECK_ARG(a->Ty > 0 && a->Hy > 0 && a->Wy > 0 && a->To > 0 && a->Ho > 0 && a->Wo > 0,
+                "ovb_tap_sum: bad extents y [%d,%d,%d] out [%d,%d,%d]", a->Ty, a->Hy, a->Wy, a->To, a->Ho, a->Wo);
+  OVB_CHECK_ARG(reinterpret_cast<uintptr_t>(a->y) % 8 == 0, "ovb_tap_sum: y must be 8-byte aligned");
+  TapSumParams p;
+  p.y = reinterpret_cast<const uint2*>(a->y);
+  p.bias = a->bias;
+  p.out = a->out;
+  p.n_taps = a->n_taps;
+  p.Ty = a->Ty; p.Hy = a->Hy; p.Wy = a->Wy;
+  p.C = a->C;
+  p.To = a->To; p.Ho = a->Ho; p.Wo = a->Wo;
+  p.clamp = a->clamp;
+  for (int k = 0; k < 27; ++k) {
+    p.dt[k] = k < a->n_taps ? a->tap_dt[k] : 0;
+    p.dh[k] = k < a->n_taps ? a->tap_dh[k] : 0;
+    p.dw[k] = k < a->n_taps ? a->tap_dw[k] : 0;
+  }
+  const long long n = static_cast<long long>(a->To) * a->Ho * a->Wo;
+  const long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(device_sm_count()) * 64;
+  tap_sum_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OVB_OK;

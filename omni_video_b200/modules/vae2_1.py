@@ -371,6 +371,13 @@ class VAEEngine:
             self._packed[name] = vae_ops.pack_conv3d(sd[name + ".weight"], sd[name + ".bias"], **kw)
         return self._packed[name]
 
+    def _head_planes(self, name: str):
+        key = (name, "planes")
+        if key not in self._packed:
+            sd = self._params()
+            self._packed[key] = vae_ops.pack_tap_planes(sd[name + ".weight"], sd[name + ".bias"])
+        return self._packed[key]
+
     def _gamma(self, name: str) -> torch.Tensor:
         if name not in self._packed:
             self._packed[name] = self._params()[name].detach().float().reshape(-1).contiguous()
@@ -624,12 +631,23 @@ class VAEEngine:
             T, Hp, W, _ = x.shape
             H = Hp - 2 * pad
             out = torch.empty((3, T, H, W), device=self.dev, dtype=f32)
-            pc_head = self._conv("decoder.head.2")
             if pad:
                 halo_fill(x, self.strip, True, True)
-            vae_ops.conv3d(x, pc_head, (T, H, W), out=out, out_strides=(H * W, W, 1), dh_shift=pad,
-                           out_mode=CONV_OUT_F32_PLANAR_CLAMP if clamp else vae_ops.CONV_OUT_F32_PLANAR,
-                           plane_stride=T * H * W)
+            if os.environ.get("OVB_HEAD_TAPSUM", "1") != "0":
+                # 96 -> 3 channels: as an implicit GEMM every MMA would fetch a full A tile for 3 useful columns.
+                # Instead ONE 1x1x1 conv (K = 96, N = 27 taps x 4) writes the per-tap partial products as planes
+                # and an HBM-bound pass shifts and adds them (ovb200.h: ovb_tap_sum)
+                pc_planes, taps, bias = self._head_planes("decoder.head.2")
+                y = torch.empty((len(taps), T, Hp, W, 4), device=self.dev, dtype=bf16)
+                vae_ops.conv3d(x, pc_planes, (T, Hp, W), out=y, out_strides=(Hp * W * 4, W * 4, 4), n_group=4,
+                               group_stride=T * Hp * W * 4)
+                vae_ops.tap_sum(y, taps, bias, 3, (T, H, W), dh_shift=pad, clamp=clamp, out=out)
+                del y
+            else:
+                vae_ops.conv3d(x, self._conv("decoder.head.2"), (T, H, W), out=out, out_strides=(H * W, W, 1),
+                               dh_shift=pad,
+                               out_mode=CONV_OUT_F32_PLANAR_CLAMP if clamp else vae_ops.CONV_OUT_F32_PLANAR,
+                               plane_stride=T * H * W)
             if self.strip is not None:  # every rank ends up with the whole clip
                 scale_h = H // (self.strip.rows(self._lat_H)[1] - self.strip.rows(self._lat_H)[0])
                 sizes = [(self.strip.rows(self._lat_H, r)[1] - self.strip.rows(self._lat_H, r)[0]) * scale_h

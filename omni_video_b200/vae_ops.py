@@ -76,6 +76,58 @@ def pack_conv3d(weight: torch.Tensor, bias: Optional[torch.Tensor], *, causal_pa
     return PackedConv(w2, bias, taps, cin, co, stride)
 
 
+def pack_tap_planes(weight: torch.Tensor, bias: Optional[torch.Tensor], *, causal_pad: Optional[int] = None):
+    """A conv with at most 4 output channels (the decoder head, 96 -> 3) as per-tap partial products:
+    returns (PackedConv of ONE 1x1x1 tap with rows k*4 + c = weight[c, :, tap k] — 4 columns per tap, zero rows up
+    to a multiple of 32 —, the taps' input offsets, the fp32 bias).  `conv3d(x, pc, n_group=4, ...)` then writes the
+    planes y[k][t][h][w][c] and `tap_sum` shifts and adds them (ovb200.h: ovb_tap_sum)."""
+    if weight.dim() == 4:
+        weight = weight.unsqueeze(2)
+    co, ci, kt, kh, kw = weight.shape
+    assert co <= 4 and ci % 16 == 0
+    cp = kt - 1 if causal_pad is None else causal_pad
+    taps = [(it - cp, ih - kh // 2, iw - kw // 2) for it in range(kt) for ih in range(kh) for iw in range(kw)]
+    n = len(taps)
+    rows = (4 * n + 31) // 32 * 32
+    w2 = torch.zeros((rows, ci), device=weight.device, dtype=bf16)
+    w = weight.detach().to(f32).reshape(co, ci, n).permute(2, 0, 1)           # [tap, Co, Ci]
+    w2[:4 * n].view(n, 4, ci)[:, :co] = w.to(bf16)
+    pc = PackedConv(w2, None, [(0, 0, 0)], ci, 4 * n)
+    return pc, taps, None if bias is None else bias.detach().to(f32).contiguous()
+
+
+def tap_sum(y: torch.Tensor, taps: Sequence[Tuple[int, int, int]], bias: Optional[torch.Tensor], channels: int,
+            out_extent: Tuple[int, int, int], *, dh_shift: int = 0, clamp: bool = False,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y: bf16 [n_taps, Ty, Hy, Wy, 4] (per-tap planes).  out[c, t, h, w] = bias[c] + sum_k y[k, t+dt, h+dh+dh_shift,
+    w+dw, c] with zero outside y's extents; fp32 [channels, To, Ho, Wo]."""
+    _need_cuda(y, bias, out)
+    lib = _lib.load()
+    n = len(taps)
+    assert y.dtype == bf16 and y.dim() == 5 and y.is_contiguous() and y.shape[0] == n and y.shape[4] == 4
+    To, Ho, Wo = out_extent
+    if out is None:
+        out = torch.empty((channels, To, Ho, Wo), device=y.device, dtype=f32)
+    assert out.dtype == f32 and out.is_contiguous() and out.numel() == channels * To * Ho * Wo
+    a = _lib.TapSumArgs()
+    a.y, a.n_taps = y.data_ptr(), n
+    dt = (C.c_int8 * n)(*[t[0] for t in taps])
+    dh = (C.c_int8 * n)(*[t[1] + dh_shift for t in taps])
+    dw = (C.c_int8 * n)(*[t[2] for t in taps])
+    a.tap_dt, a.tap_dh, a.tap_dw = (C.cast(v, C.POINTER(C.c_int8)) for v in (dt, dh, dw))
+    a.Ty, a.Hy, a.Wy = y.shape[1], y.shape[2], y.shape[3]
+    if bias is not None:
+        assert bias.dtype == f32 and bias.numel() == channels
+        a.bias = bias.data_ptr()
+    a.out, a.C = out.data_ptr(), channels
+    a.To, a.Ho, a.Wo = To, Ho, Wo
+    a.clamp = int(clamp)
+    ev = ops_mod._tl_begin()
+    _lib.check(lib.ovb_tap_sum(C.byref(a), _stream()), "ovb_tap_sum")
+    ops_mod._tl_end(ev, "tap_sum", float(To * Ho * Wo) * (8 * n + 4 * channels), (To, Ho, Wo, n, channels))
+    return out
+
+
 def pack_upsample_conv2d(weight: torch.Tensor, bias: Optional[torch.Tensor]):
     """nearest-2x upsample followed by Conv2d(3x3, padding=1) (reference vae2_1.py:75-84) as FOUR
     2x2 convolutions on the low-resolution input, one per output phase (a, b) in {0,1}^2:

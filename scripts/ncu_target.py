@@ -1,5 +1,5 @@
 """Small single-kernel targets for `ncu --set full` captures.
-    python scripts/ncu_target.py attn|attn_b2|gemm|gemm_resid|conv96|conv192|norm|ln|rope
+    python scripts/ncu_target.py attn|attn_b2|gemm|gemm_resid|conv96|conv192|head|norm|ln|rope
 """
 import math
 import os
@@ -39,6 +39,18 @@ elif what in ("conv96", "conv192"):
     wt = torch.randn(c, c, 3, 3, 3, device="cuda") / math.sqrt(27 * c)
     pc = vae_ops.pack_conv3d(wt, torch.zeros(c, device="cuda"))
     fn = lambda: vae_ops.conv3d(x, pc, (T, H, W))  # noqa: E731
+elif what == "head":
+    # the decoder head as per-tap planes (1x1x1 conv, n_group = 4) + tap_sum: two launches
+    T, H, W = 9, 480, 832
+    x = torch.randn(T, H, W, 96, device="cuda").to(bf16)
+    pc, taps, bias = vae_ops.pack_tap_planes(torch.randn(3, 96, 3, 3, 3, device="cuda") / math.sqrt(27 * 96),
+                                             torch.zeros(3, device="cuda"))
+    y = torch.empty((27, T, H, W, 4), device="cuda", dtype=bf16)
+    o = torch.empty((3, T, H, W), device="cuda")
+
+    def fn():
+        vae_ops.conv3d(x, pc, (T, H, W), out=y, out_strides=(H * W * 4, W * 4, 4), n_group=4, group_stride=T * H * W * 4)
+        vae_ops.tap_sum(y, taps, bias, 3, (T, H, W), clamp=True, out=o)
 elif what == "ln":
     L, d = 65520, 1536
     x = torch.randn(L, d, device="cuda")

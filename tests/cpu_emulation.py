@@ -215,6 +215,32 @@ def conv3d(x, pc, out_extent, *, out=None, out_strides=None, out_base=0, n_group
     return out
 
 
+def tap_sum(y, taps, bias, channels, out_extent, *, dh_shift=0, clamp=False, out=None):
+    """ovb_tap_sum (include/ovb200.h): out[c,t,h,w] = bias[c] + sum_k y[k, t+dt, h+dh+dh_shift, w+dw, c], zero outside."""
+    n, Ty, Hy, Wy, _ = y.shape
+    To, Ho, Wo = out_extent
+    t = torch.arange(To).view(To, 1, 1)
+    h = torch.arange(Ho).view(1, Ho, 1)
+    w = torch.arange(Wo).view(1, 1, Wo)
+    acc = torch.zeros((To, Ho, Wo, 4), dtype=f32)
+    for k, (dt, dh, dw) in enumerate(taps):
+        ti, hi, wi = t + dt, h + dh + dh_shift, w + dw
+        ok = ((ti >= 0) & (ti < Ty)) & ((hi >= 0) & (hi < Hy)) & ((wi >= 0) & (wi < Wy))
+        ti, hi, wi = (ti.clamp(0, Ty - 1).expand(To, Ho, Wo), hi.clamp(0, Hy - 1).expand(To, Ho, Wo),
+                      wi.clamp(0, Wy - 1).expand(To, Ho, Wo))
+        acc += y[k].float()[ti, hi, wi] * ok.unsqueeze(-1)
+    r = acc[..., :channels]
+    if bias is not None:
+        r = r + bias.float()
+    if clamp:
+        r = r.clamp(-1.0, 1.0)
+    r = r.permute(3, 0, 1, 2).contiguous()
+    if out is None:
+        return r
+    out.copy_(r)
+    return out
+
+
 def rmsnorm_silu(x, gamma, silu=True, out=None):
     xf = x.float()
     y = xf / xf.norm(dim=-1, keepdim=True).clamp_min(1e-12) * (x.shape[-1] ** 0.5) * gamma.float()
@@ -252,6 +278,6 @@ def install_vae(monkeypatch):
     from omni_video_b200.modules.vae2_1 import VAEEngine
     install(monkeypatch)
     monkeypatch.setattr(VAEEngine, "_check_device", staticmethod(lambda dev: None))
-    for name, fn in dict(conv3d=conv3d, rmsnorm_silu=rmsnorm_silu, planar_to_cl=planar_to_cl, cl_to_planar=cl_to_planar,
+    for name, fn in dict(conv3d=conv3d, tap_sum=tap_sum, rmsnorm_silu=rmsnorm_silu, planar_to_cl=planar_to_cl, cl_to_planar=cl_to_planar,
                          softmax_rows=softmax_rows).items():
         monkeypatch.setattr(vae_ops, name, fn)

@@ -201,6 +201,47 @@ def test_head_conv_planar_clamped(vops):
     assert (out.cpu() - ref).abs().max().item() <= 2e-3
 
 
+@pytest.mark.parametrize("T,H,W,pad", [(2, 9, 14, 0), (5, 17, 40, 0), (3, 10, 24, 1)])
+def test_head_conv_as_tap_planes_and_tap_sum(vops, T, H, W, pad):
+    """The 96 -> 3 head conv (vae2_1.py:164-165) as one 1x1x1 conv writing per-tap partial products as planes
+    (n_group = 4) + ovb_tap_sum: against the fp32 conv, against the implicit-GEMM form of the same conv (the partial
+    products are rounded to bf16: a few 1e-3 of the value range), and with one halo row above and below the
+    strip (pad = 1: the conv runs over the halo rows as well, tap_sum shifts its row offsets)."""
+    rng = _rng(60 + T)
+    c = 96
+    x = _randn(rng, c, T, H, W).to(bf16).float()
+    w = _randn(rng, 3, c, 3, 3, 3, scale=3.0 * (27 * c) ** -0.5).to(bf16).float()
+    b = _randn(rng, 3, scale=0.1)
+    ref = V.causal_conv3d(x, w, b)
+    xin = x
+    if pad:   # strip layout: one halo row above and below; a halo row of zeros == the image border
+        xin = F.pad(x, (0, 0, 1, 1))
+    Hp = H + 2 * pad
+    pc, taps, bias = vops.pack_tap_planes(w.cuda(), b.cuda())
+    assert pc.w.shape == (128, c) and pc.cout == 108 and len(taps) == 27
+    y = torch.full((27, T, Hp, W, 4), float("nan"), device="cuda", dtype=bf16)
+    vops.conv3d(_cl(xin), pc, (T, Hp, W), out=y, out_strides=(Hp * W * 4, W * 4, 4), n_group=4,
+                group_stride=T * Hp * W * 4)
+    assert bool(torch.isfinite(y).all())                      # every plane element written
+    # plane k is x . W[:, :, tap k]
+    k = 14
+    wk = w.reshape(3, c, 27)[:, :, k]
+    yk = torch.einsum("cthw,oc->thwo", xin, wk)
+    assert (y[k, ..., :3].float().cpu() - yk).abs().max().item() <= 2e-2 * yk.abs().max().item()
+    assert float(y[..., 3].abs().max()) == 0.0
+    for clamp in (False, True):
+        out = vops.tap_sum(y, taps, bias, 3, (T, H, W), dh_shift=pad, clamp=clamp)
+        want = ref.clamp(-1, 1) if clamp else ref
+        assert (out.cpu() - want).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item())
+    direct = torch.empty((3, T, H, W), device="cuda", dtype=torch.float32)
+    vops.conv3d(_cl(xin), vops.pack_conv3d(w.cuda(), b.cuda()), (T, H, W), out=direct, out_strides=(H * W, W, 1),
+                dh_shift=pad, out_mode=vops.CONV_OUT_F32_PLANAR, plane_stride=T * H * W)
+    out = vops.tap_sum(y, taps, bias, 3, (T, H, W), dh_shift=pad)
+    rel = ((out - direct).norm() / direct.norm()).item()
+    print(f"head conv as tap planes + tap_sum vs implicit GEMM: rel-L2 {rel:.2e}")
+    assert rel <= 3e-3
+
+
 @pytest.mark.parametrize("c", [16, 96, 192, 384, 768])
 def test_rmsnorm_silu_cl(vops, c):
     rng = _rng(c)
