@@ -362,13 +362,15 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           col_ok = col < p.Cout;
           const int grp = col / p.n_group;
           coff = grp * p.group_stride + (col - grp * p.n_group);
-          uint2 xb[8];  // residual values, requested up front
+          uint2 xb[8];  // residual values, requested up front.  The loads are UNCONDITIONAL (voxels or columns
+          // outside the tensor read element 0; their results are never stored): a predicated load needs a
+          // select behind it, and ptxas then waits for each load before it issues the next — eight serialised
+          // DRAM latencies per chunk, which made the residual forms epilogue-bound (ncu source page, round 2).
           if (has_resid) {
+            const long long csafe = col_ok ? coff : 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              xb[i] = make_uint2(0u, 0u);
-              if (col_ok && vbase[i] >= 0) xb[i] = *reinterpret_cast<const uint2*>(p.resid + vbase[i] + coff);
-            }
+            for (int i = 0; i < 8; ++i)
+              xb[i] = *reinterpret_cast<const uint2*>(p.resid + (vbase[i] >= 0 ? vbase[i] : 0) + csafe);
           }
           float b4[4] = {0.f, 0.f, 0.f, 0.f};
           if (p.bias != nullptr && col_ok) {

@@ -1,5 +1,5 @@
 """Small single-kernel targets for `ncu --set full` captures.
-    python scripts/ncu_target.py attn|attn_b2|gemm|gemm_resid|conv96|conv192|head|norm|ln|rope
+    python scripts/ncu_target.py attn|attn_b2|gemm|gemm_resid|conv96|conv96_dual|conv192|head|norm|ln|rope
 """
 import math
 import os
@@ -39,6 +39,15 @@ elif what in ("conv96", "conv192"):
     wt = torch.randn(c, c, 3, 3, 3, device="cuda") / math.sqrt(27 * c)
     pc = vae_ops.pack_conv3d(wt, torch.zeros(c, device="cuda"))
     fn = lambda: vae_ops.conv3d(x, pc, (T, H, W))  # noqa: E731
+elif what == "conv96_dual":
+    # second conv of a 96-channel residual block: + residual, raw sum AND its RMS_norm.SiLU written (two tensors)
+    T, H, W, c = 9, 480, 832, 96
+    x = torch.randn(T, H, W, c, device="cuda").to(bf16)
+    res = torch.randn(T, H, W, c, device="cuda").to(bf16)
+    pc = vae_ops.pack_conv3d(torch.randn(c, c, 3, 3, 3, device="cuda") / math.sqrt(27 * c), torch.zeros(c, device="cuda"))
+    gamma = torch.ones(c, device="cuda")
+    o, on = torch.empty_like(x), torch.empty_like(x)
+    fn = lambda: vae_ops.conv3d(x, pc, (T, H, W), out=o, resid=res, norm_gamma=gamma, norm_out=on)  # noqa: E731
 elif what == "head":
     # the decoder head as per-tap planes (1x1x1 conv, n_group = 4) + tap_sum: two launches
     T, H, W = 9, 480, 832
