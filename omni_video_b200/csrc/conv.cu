@@ -372,10 +372,11 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i = 0; i < 8; ++i)
               xb[i] = *reinterpret_cast<const uint2*>(p.resid + (vbase[i] >= 0 ? vbase[i] : 0) + csafe);
           }
-          float b4[4] = {0.f, 0.f, 0.f, 0.f};
+          uint64_t b01 = 0, b23 = 0;  // bias of this lane's 4 columns as two fp32 pairs
           if (p.bias != nullptr && col_ok) {
             const float4 bv = *reinterpret_cast<const float4*>(p.bias + col);
-            b4[0] = bv.x; b4[1] = bv.y; b4[2] = bv.z; b4[3] = bv.w;
+            b01 = pack_f32x2(bv.x, bv.y);
+            b23 = pack_f32x2(bv.z, bv.w);
           }
           tmem_wait_ld();
 #pragma unroll
@@ -386,26 +387,30 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                          : "memory");
           }
           __syncwarp();
+          // Packed arithmetic throughout (one epilogue warp per scheduler: the instruction count is the
+          // cost): fp32x2 bias add, one cvt per pair, and the residual added as bf16x2 — the exact sum of
+          // the bf16-rounded conv result and the bf16 residual, rounded once to bf16.
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + rr_off;
             const uint32_t a = stg_addr + rr * 128 + ((cj ^ (rr & 7)) << 4);
-            uint32_t u0, u1, u2, u3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
-                         : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
-                         : "r"(a)
-                         : "memory");
-            float f0 = __uint_as_float(u0) + b4[0], f1 = __uint_as_float(u1) + b4[1];
-            float f2 = __uint_as_float(u2) + b4[2], f3 = __uint_as_float(u3) + b4[3];
+            uint64_t u01, u23;
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];\n" : "=l"(u01), "=l"(u23) : "r"(a) : "memory");
+            float f0, f1, f2, f3;
+            unpack_f32x2(fadd2(u01, b01), f0, f1);
+            unpack_f32x2(fadd2(u23, b23), f2, f3);
+            uint32_t c01 = pack_bf16x2(f0, f1), c23 = pack_bf16x2(f2, f3);
             if (has_resid) {
-              const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].x));
-              const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb[i].y));
               // conv result is stored as bf16 before the add in the unfused formulation
-              f0 = bf16_round(f0) + a0.x; f1 = bf16_round(f1) + a0.y;
-              f2 = bf16_round(f2) + a1.x; f3 = bf16_round(f3) + a1.y;
+              const __nv_bfloat162 s01 = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&c01),
+                                                 *reinterpret_cast<const __nv_bfloat162*>(&xb[i].x));
+              const __nv_bfloat162 s23 = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&c23),
+                                                 *reinterpret_cast<const __nv_bfloat162*>(&xb[i].y));
+              c01 = *reinterpret_cast<const uint32_t*>(&s01);
+              c23 = *reinterpret_cast<const uint32_t*>(&s23);
             }
-            o8[i].x = pack_bf16x2(f0, f1);
-            o8[i].y = pack_bf16x2(f2, f3);
+            o8[i].x = c01;
+            o8[i].y = c23;
           }
           __syncwarp();
         };
@@ -422,30 +427,41 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           sq += __shfl_xor_sync(0xffffffffu, sq, 4);
           return sq;
         };
-        auto normalised = [&](const uint2 o, const float inv, const float (&g4)[4]) {
+        // g01/g23: gamma of this lane's 4 columns, halved when SiLU follows: SiLU(y) = h + h tanh(h), h = y/2
+        // (as rmsnorm_silu_cl_kernel; the factor 1/2 is exact, so (r*inv)*(g/2) == ((r*inv)*g)/2 bit for bit)
+        auto normalised = [&](const uint2 o, const float inv, const uint64_t g01, const uint64_t g23) {
           const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
           const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.y));
-          float y[4] = {r01.x * inv * g4[0], r01.y * inv * g4[1], r23.x * inv * g4[2], r23.y * inv * g4[3]};
+          const uint64_t inv2 = pack_f32x2(inv, inv);
+          uint64_t h01 = fmul2(fmul2(pack_f32x2(r01.x, r01.y), inv2), g01);
+          uint64_t h23 = fmul2(fmul2(pack_f32x2(r23.x, r23.y), inv2), g23);
           if (p.norm_silu) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {  // SiLU(y) = h + h tanh(h), h = y/2 (as rmsnorm_silu_cl_kernel)
-              const float h = 0.5f * y[j];
-              float th;
-              asm("tanh.approx.f32 %0, %1;\n" : "=f"(th) : "f"(h));
-              y[j] = fmaf(h, th, h);
-            }
+            float h0, h1, h2, h3, t0, t1, t2, t3;
+            unpack_f32x2(h01, h0, h1);
+            unpack_f32x2(h23, h2, h3);
+            asm("tanh.approx.f32 %0, %1;\n" : "=f"(t0) : "f"(h0));
+            asm("tanh.approx.f32 %0, %1;\n" : "=f"(t1) : "f"(h1));
+            asm("tanh.approx.f32 %0, %1;\n" : "=f"(t2) : "f"(h2));
+            asm("tanh.approx.f32 %0, %1;\n" : "=f"(t3) : "f"(h3));
+            h01 = ffma2(h01, pack_f32x2(t0, t1), h01);
+            h23 = ffma2(h23, pack_f32x2(t2, t3), h23);
           }
+          float y0, y1, y2, y3;
+          unpack_f32x2(h01, y0, y1);
+          unpack_f32x2(h23, y2, y3);
           uint2 r;
-          r.x = pack_bf16x2(y[0], y[1]);
-          r.y = pack_bf16x2(y[2], y[3]);
+          r.x = pack_bf16x2(y0, y1);
+          r.y = pack_bf16x2(y2, y3);
           return r;
         };
-        auto load_gamma = [&](const int c, float (&g4)[4]) {
+        auto load_gamma = [&](const int c, uint64_t& g01, uint64_t& g23) {
           const int col = nt * p.BN + c * 32 + cj * 4;
-          g4[0] = g4[1] = g4[2] = g4[3] = 0.f;
+          g01 = g23 = 0;
           if (col < p.Cout) {
             const float4 gv = *reinterpret_cast<const float4*>(p.norm_gamma + col);
-            g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
+            const float k = p.norm_silu ? 0.5f : 1.0f;
+            g01 = pack_f32x2(k * gv.x, k * gv.y);
+            g23 = pack_f32x2(k * gv.z, k * gv.w);
           }
         };
         const float sqrt_c = sqrtf(static_cast<float>(p.Cout));
@@ -488,12 +504,12 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const int col = nt * p.BN + c * 32 + cj * 4;
               const int grp = col / p.n_group;
               const long long coff = grp * p.group_stride + (col - grp * p.n_group);
-              float g4[4];
-              load_gamma(c, g4);
+              uint64_t g01, g23;
+              load_gamma(c, g01, g23);
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (col < p.Cout && vbase[i] >= 0)
-                  *reinterpret_cast<uint2*>(out_nrm + vbase[i] + coff) = normalised(keep[c][i], ss[i], g4);
+                  *reinterpret_cast<uint2*>(out_nrm + vbase[i] + coff) = normalised(keep[c][i], ss[i], g01, g23);
             }
           }
         } else {
@@ -515,13 +531,13 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 8; ++i) ss[i] += sumsq4(o8[i], col_ok);
               } else {
-                float g4[4];
-                load_gamma(c, g4);
+                uint64_t g01, g23;
+                load_gamma(c, g01, g23);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   if (col_ok && vbase[i] >= 0) {
                     if (out_raw != nullptr) *reinterpret_cast<uint2*>(out_raw + vbase[i] + coff) = o8[i];
-                    *reinterpret_cast<uint2*>(out_nrm + vbase[i] + coff) = normalised(o8[i], ss[i], g4);
+                    *reinterpret_cast<uint2*>(out_nrm + vbase[i] + coff) = normalised(o8[i], ss[i], g01, g23);
                   }
                 }
               }
