@@ -340,7 +340,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // residual box two chunks ahead, each thread reads ITS row from the box (TMA's 128-byte swizzle is
 // conflict free for row-per-thread 16-byte accesses), writes the result back in place, and the box
 // goes to `out` with one TMA store.  Main loop as above with a 4-stage operand ring.
-constexpr int kRStages = 4;                       // operand ring
+// 5 operand stages + 4 residual boxes fill the 227 KB (4 stages: FFN2 [65520,1536,8960] 1.30 ms, 5: 1.17 ms =
+// the plain bf16 epilogue's time; O-projection 0.271 -> 0.252 ms).  Pulling the next tile's residual columns into
+// L2 ahead of time (cp.async.bulk.prefetch.tensor) was measured too and made both shapes 2-8 % slower.
+constexpr int kRStages = 5;                       // operand ring
 constexpr int kRing = 4;                          // residual boxes
 constexpr int kRBoxBytes = kBM * 32 * 4;          // 16 KB
 constexpr int kGemmResidSmem = kRStages * kStageBytes + kRing * kRBoxBytes + 1024 + 256;
@@ -515,8 +518,11 @@ gemm_resid_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN + c * 32, v);
-        // bias and gate for these 32 columns (same for every row of a sample: L1 broadcast)
-        float bsv[32], gtv[32];
+        // bias and gate for these 32 columns (same for every row of a sample: L1 broadcast), kept as fp32
+        // pairs: the update below is packed (FADD2, one cvt per pair, FFMA2) — this warp is alone on its
+        // scheduler and the instruction count per chunk decides whether the epilogue hides behind a
+        // K = 1536 main loop
+        uint64_t bs2[16], gt2[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           if (p.bias != nullptr && col0 + j < p.N) {
@@ -525,19 +531,19 @@ gemm_resid_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float2 f = __bfloat1622float2(b2[q]);
-              bsv[j + 2 * q] = f.x;
-              bsv[j + 2 * q + 1] = f.y;
+              bs2[j / 2 + q] = pack_f32x2(f.x, f.y);
             }
           } else {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) bsv[j + q] = 0.f;
+            for (int q = 0; q < 4; ++q) bs2[j / 2 + q] = 0;
           }
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 gq = make_float4(1.f, 1.f, 1.f, 1.f);
           if (kGate && col0 + j < p.N) gq = *reinterpret_cast<const float4*>(gate_row + col0 + j);
-          gtv[j] = gq.x; gtv[j + 1] = gq.y; gtv[j + 2] = gq.z; gtv[j + 3] = gq.w;
+          gt2[j / 2] = pack_f32x2(gq.x, gq.y);
+          gt2[j / 2 + 1] = pack_f32x2(gq.z, gq.w);
         }
         mbar_wait(&rfull_bar[b], static_cast<uint32_t>((g / kRing) & 1));
         tmem_wait_ld();
@@ -545,18 +551,16 @@ gemm_resid_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t a = row_addr + ((j ^ (r_in_cta & 7)) << 4);
-          float x0, x1, x2, x3;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
-                       : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3)
-                       : "r"(a)
-                       : "memory");
-          x0 += bf16_round(__uint_as_float(v[4 * j]) + bsv[4 * j]) * gtv[4 * j];
-          x1 += bf16_round(__uint_as_float(v[4 * j + 1]) + bsv[4 * j + 1]) * gtv[4 * j + 1];
-          x2 += bf16_round(__uint_as_float(v[4 * j + 2]) + bsv[4 * j + 2]) * gtv[4 * j + 2];
-          x3 += bf16_round(__uint_as_float(v[4 * j + 3]) + bsv[4 * j + 3]) * gtv[4 * j + 3];
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "f"(x0), "f"(x1), "f"(x2),
-                       "f"(x3)
-                       : "memory");
+          uint64_t x01, x23;
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];\n" : "=l"(x01), "=l"(x23) : "r"(a) : "memory");
+          // x += bf16(acc + bias) * gate, two columns per instruction
+          float s0, s1, s2, s3;
+          unpack_f32x2(fadd2(pack_f32x2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), bs2[2 * j]), s0, s1);
+          unpack_f32x2(fadd2(pack_f32x2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), bs2[2 * j + 1]), s2, s3);
+          const uint32_t c01 = pack_bf16x2(s0, s1), c23 = pack_bf16x2(s2, s3);
+          x01 = ffma2(pack_f32x2(__uint_as_float(c01 << 16), __uint_as_float(c01 & 0xffff0000u)), gt2[2 * j], x01);
+          x23 = ffma2(pack_f32x2(__uint_as_float(c23 << 16), __uint_as_float(c23 & 0xffff0000u)), gt2[2 * j + 1], x23);
+          asm volatile("st.shared.v2.b64 [%0], {%1, %2};\n" ::"r"(a), "l"(x01), "l"(x23) : "memory");
         }
         fence_proxy_async_smem();      // generic-proxy writes visible to the TMA store
         named_bar_sync(1, 128);        // all four epilogue warps have written their rows

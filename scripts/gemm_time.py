@@ -39,5 +39,7 @@ for M, N, K in [(65520, 8960, 1536), (65520, 4608, 1536), (65520, 1536, 8960), (
                      ("gelu", lambda: ops.gemm(a, w, b, epilogue=ops.EPI_GELU_BF16, out=o)),
                      ("gate+resid f32", lambda: ops.gemm(a, w, b, epilogue=ops.EPI_GATE_RESID_F32, out=x, resid=x, gate=g,
                                                          rows_per_sample=M // 2))]:
+        if os.environ.get("GEMM_ONLY") and os.environ["GEMM_ONLY"] not in name:
+            continue
         ms = t(fn)
         print(f"gemm [{M},{N},{K}] {name}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s", flush=True)

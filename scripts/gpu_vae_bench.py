@@ -28,6 +28,20 @@ def vae_decode_flops(T, h, w):
     return (0.688e9 + 2.162e9 * (T - 1)) * h * w + 4.0 * (h * w) ** 2 * 384 * T
 
 
+def print_timeline():
+    tl, ops.timeline = ops.timeline, None
+    agg = collections.OrderedDict()
+    for kind, work, shape, s, e in tl:
+        a = agg.setdefault((kind,) + tuple(shape), [0, 0.0, 0.0])
+        a[0] += 1; a[1] += s.elapsed_time(e); a[2] += work
+    tot = sum(a[1] for a in agg.values())
+    print(f"timed launches total {tot:.1f} ms")
+    for k, (n, ms, work) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+        rate = work / ms / 1e9
+        unit = "TF/s" if k[0] in ("conv", "gemm", "attn") else "GB/s*1e-3"
+        print(f"  {ms:8.2f} ms {100 * ms / tot:5.1f}% n={n:3d} {rate:8.1f} {unit}  {k}")
+
+
 def main():
     video = arg("--video", "480p")
     T = int(arg("--frames", "21"))
@@ -55,22 +69,14 @@ def main():
               f"{vae_decode_flops(T, h, w) / ms / 1e9:.0f} TF/s algorithmic, out {tuple(out.shape)} "
               f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
         res["decode_ms"] = ms
-    tl, ops.timeline = ops.timeline, None
-    agg = collections.OrderedDict()
-    for kind, work, shape, s, e in tl:
-        a = agg.setdefault((kind,) + tuple(shape), [0, 0.0, 0.0])
-        a[0] += 1; a[1] += s.elapsed_time(e); a[2] += work
-    tot = sum(a[1] for a in agg.values())
-    print(f"timed launches total {tot:.1f} ms")
-    for k, (n, ms, work) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
-        rate = work / ms / 1e9
-        unit = "TF/s" if k[0] in ("conv", "gemm", "attn") else "GB/s*1e-3"
-        print(f"  {ms:8.2f} ms {100 * ms / tot:5.1f}% n={n:3d} {rate:8.1f} {unit}  {k}")
+    print_timeline()
     del out
     if "--encode" in sys.argv:
         Tv = 1 + 4 * (T - 1)
         v = torch.rand((3, Tv, 8 * h, 8 * w), generator=g, device="cuda") * 2 - 1
-        for it in range(2):
+        for it in range(3):
+            torch.cuda.synchronize()
+            ops.timeline = [] if it == 2 else None
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             mu = vae.encode([v])[0]
@@ -78,6 +84,7 @@ def main():
             torch.cuda.synchronize()
             print(f"encode {video} T={Tv}: {e0.elapsed_time(e1):.1f} ms out {tuple(mu.shape)}", flush=True)
             res["encode_ms"] = e0.elapsed_time(e1)
+        print_timeline()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"vae_bench_{video}.json"), "w") as f:
         json.dump(res, f)
