@@ -50,4 +50,6 @@ def test_t5_encoder_at_umt5_xxl_width_vs_oracle():
     for b, n in enumerate(lengths):
         err = O.rel_l2(out[b, :n].float().cpu(), want[b])
         print(f"umT5-XXL width, {n} tokens: rel-L2 vs fp32 oracle {err:.3e}")
-        assert bool(torch.isfinite(out[b, :n].float()).all()) and err <= 2.5e-2
+        # at the real width the averaging over 4096 channels brings the bf16 error under the north-star bound
+        # (measured 8.4e-3 / 9.0e-3); the toy cases above keep 2.5e-2 (dim 128, sharp unscaled softmaxes)
+        assert bool(torch.isfinite(out[b, :n].float()).all()) and err <= 1e-2
