@@ -31,7 +31,7 @@ extern "C" {
 #define OVB_ERR_CUDA (-2)
 #define OVB_ERR_UNSUPPORTED_ARCH (-3)
 
-#define OVB_ABI_VERSION 3
+#define OVB_ABI_VERSION 4
 
 /* ---- library ---------------------------------------------------------------------------- */
 int ovb_abi_version(void);
@@ -140,6 +140,32 @@ int64_t ovb_attn_workspace_size(const ovb_attn_args* args);
  * no_split): n_whole items run as one CTA each, the n_tail items of the last partial wave are cut
  * `parts` ways along the keys (n_tail = 0, parts = 1: no split).  Launches nothing. */
 int ovb_attn_plan(const ovb_attn_args* args, int32_t* n_whole, int32_t* n_tail, int32_t* parts);
+
+/* ---- attention with a relative-position bias (umT5 encoder; warp-level mma.sync, bf16) --------------
+ * out[b, i, h, :] = softmax_j( scale * <q[b,i,h,:], k[b,j,h,:]> + rel_bias[h, (j - i) + L - 1], j < k_lens[b] )
+ *                   * v[b, j, h, :]
+ * All heads and samples in ONE launch.  Replaces T5Attention.forward's score / bias / mask / softmax / PV chain
+ * (reference omnivideo/modules/t5.py:96-117; umT5 uses scale = 1, t5.py:101) with the bias of
+ * T5RelativeEmbedding (t5.py:229-263), which depends on (j - i) only: rel_bias is fp32 [H, >= 2L-1], head h at
+ * rel_bias + h * bias_head_stride.  fp32 scores and softmax statistics, P rounded to bf16 before P V, fp32
+ * accumulation.  q/k/v/out are [B, L, H, head_dim] views addressed as in ovb_attn_args (so they may be column
+ * blocks of one fused [B*L, 3*H*head_dim] projection); head_dim 64 or 128.
+ * k_lens: DEVICE pointer to B int32 (valid keys per sample, clamped to [1, L]) or NULL (= L): no host
+ * synchronisation is needed to encode a ragged batch.  Rows i >= k_lens[b] are computed like the reference does
+ * (they attend the valid keys); the caller drops them.
+ */
+typedef struct ovb_attn_relbias_args {
+  const void* q; int64_t q_row_stride; int64_t q_batch_stride;
+  const void* k; int64_t k_row_stride; int64_t k_batch_stride;
+  const void* v; int64_t v_row_stride; int64_t v_batch_stride;
+  void* out;     int64_t o_row_stride; int64_t o_batch_stride;
+  const float* rel_bias; int64_t bias_head_stride;
+  const int32_t* k_lens;  /* device, may be NULL */
+  int32_t B, H, L, head_dim;
+  float softmax_scale;
+} ovb_attn_relbias_args;
+
+int ovb_attn_relbias_fwd(const ovb_attn_relbias_args* args, void* stream);
 
 /* ---- peer transport: cross-GPU signal / wait ---------------------------------------------------
  * Every rank owns a pad of >= world uint32 flags in memory that all ranks have mapped

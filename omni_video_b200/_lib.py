@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OVB_LIB_PATH") or os.path.join(_HERE, "libovb200.so")
 
 OVB_OK = 0
-ABI_VERSION = 3   # include/ovb200.h OVB_ABI_VERSION
+ABI_VERSION = 4   # include/ovb200.h OVB_ABI_VERSION
 
 # epilogues / modes (mirror include/ovb200.h)
 EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_GATE_RESID_F32, EPI_F32, EPI_RESID_BF16 = range(6)
@@ -48,6 +48,19 @@ class AttnArgs(C.Structure):
         ("softmax_scale", C.c_float),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("no_split", C.c_int32),
         ("out_ptrs", C.POINTER(C.c_void_p)), ("n_out_ptrs", C.c_int32), ("rows_per_out", C.c_int32),
+    ]
+
+
+class AttnRelBiasArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
+        ("k", C.c_void_p), ("k_row_stride", C.c_int64), ("k_batch_stride", C.c_int64),
+        ("v", C.c_void_p), ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
+        ("out", C.c_void_p), ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
+        ("rel_bias", C.c_void_p), ("bias_head_stride", C.c_int64),
+        ("k_lens", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("L", C.c_int32), ("head_dim", C.c_int32),
+        ("softmax_scale", C.c_float),
     ]
 
 
@@ -132,6 +145,7 @@ _SIGNATURES = {
     "ovb_attn_workspace_size": (C.c_int64, [C.POINTER(AttnArgs)]),
     "ovb_attn_plan": (C.c_int, [C.POINTER(AttnArgs), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int32)]),
+    "ovb_attn_relbias_fwd": (C.c_int, [C.POINTER(AttnRelBiasArgs), C.c_void_p]),
     "ovb_peer_signal_wait": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "ovb_enable_peer_access": (C.c_int, [C.c_int32]),

@@ -12,36 +12,35 @@ working without PyTorch arithmetic on the device.  Parameter names are the refer
     reference (t5.py)                                            kernel
     -----------------------------------------------------------  ------------------------------------------
     T5LayerNorm :55-64 (RMS, cast to bf16 before the weight)     ovb_rmsnorm_rope (rope = 0)
-    q | k = x W^T (no bias) :96-98                               ovb_gemm_bf16 (fused [Wq; Wk])
-    V^T = Wv x^T                                                 ovb_gemm_bf16 (A = Wv, W = x: no transpose copy)
-    scores + position bias + key mask :101-110 (NO 1/sqrt(d))    ovb_gemm_bf16 RESID_F32 into a buffer preloaded
-                                                                 with the [L, keys] bias (-3e38 on padding keys)
-    softmax in fp32 :111                                         ovb_softmax_rows
-    P V, o-projection + residual :112-117, :169                  ovb_gemm_bf16, ovb_gemm_bf16 RESID_BF16
+    q | k | v = x W^T (no bias) :96-98                           ovb_gemm_bf16 (fused [Wq; Wk; Wv], whole batch)
+    scores + position bias + key mask, fp32 softmax, P V         ovb_attn_relbias_fwd: all heads and samples in ONE
+      :101-112 (NO 1/sqrt(d))                                    launch, per-sample key counts read on the device
+    o-projection + residual :113-117, :169                       ovb_gemm_bf16 RESID_BF16
     fc1(x) * GELU_tanh(gate(x)) :133-138                         ovb_gemm_bf16 GELU_BF16 -> fp32 gate table ->
                                                                  ovb_gemm_bf16 GATE_RESID_F32 on a zero residual
     fc2 + residual :170                                          ovb_gemm_bf16 RESID_BF16
 
-The relative-position bucket table (t5.py:241-263) is integer arithmetic on positions: computed once per
-sequence length on the host, like the reference does.
+A block is 12 launches whatever the head count (round 1 looped over the heads: 4 launches x 64 heads x 24 blocks).
+The relative-position bias (t5.py:229-263) depends on (key - query) only: per block it is an fp32 [heads, 2L-1]
+vector table, gathered once per sequence length from the bucket embedding (integer arithmetic on positions, on the
+host, like the reference does) and cached next to the packed weights.
 """
 from __future__ import annotations
 
 import logging
 import math
-from typing import List
+from typing import List, Optional
 
 import torch
 import torch.nn as nn
 
-from .. import ops, vae_ops
-from ..ops import EPI_BF16, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_RESID_BF16, EPI_RESID_F32
+from .. import ops
+from ..ops import EPI_BF16, EPI_GATE_RESID_F32, EPI_GELU_BF16, EPI_RESID_BF16
 
 __all__ = ["T5Encoder", "T5EncoderModel", "umt5_xxl"]
 
 bf16 = torch.bfloat16
 f32 = torch.float32
-_NEG = -3.0e38          # additive mask for padding keys (the reference uses finfo.min, t5.py:108)
 
 
 class T5LayerNorm(nn.Module):
@@ -90,6 +89,11 @@ class T5RelativeEmbedding(nn.Module):
         far = torch.minimum(far, torch.full_like(far, half - 1))
         return out + torch.where(rel < exact, rel, far)
 
+    def relative_buckets(self, L: int) -> torch.Tensor:
+        """[2L-1] int64: bucket of (key - query) = -(L-1) .. L-1, i.e. `buckets(L, L)[i, j]` at index (j - i) + L - 1."""
+        b = self.buckets(L, L)
+        return torch.cat([b[L - 1, :L - 1], b[0]])
+
 
 class T5SelfAttention(nn.Module):
     def __init__(self, dim, dim_attn, dim_ffn, num_heads, num_buckets, shared_pos=True, dropout=0.1):
@@ -121,81 +125,86 @@ class T5Encoder(nn.Module):
         self.norm = T5LayerNorm(dim)
         self._packed = None
         self._bucket_cache = {}
+        self._bias_cache = {}
 
-    # packed bf16 weights (fused [Wq; Wk]): a derived cache, rebuilt when parameters move or change
+    # packed bf16 weights (fused [Wq; Wk; Wv]): a derived cache, rebuilt when parameters move or change
     def _weights(self):
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed is None or self._packed[0] != key:
             layers = []
             for blk in self.blocks:
                 a, f = blk.attn, blk.ffn
-                layers.append(dict(n1=_w(blk.norm1.weight), qk=_w(torch.cat([a.q.weight, a.k.weight], 0)), v=_w(a.v.weight),
+                layers.append(dict(n1=_w(blk.norm1.weight), qkv=_w(torch.cat([a.q.weight, a.k.weight, a.v.weight], 0)),
                                    o=_w(a.o.weight), n2=_w(blk.norm2.weight), gate=_w(f.gate[0].weight),
                                    fc1=_w(f.fc1.weight), fc2=_w(f.fc2.weight)))
             self._packed = (key, layers, _w(self.norm.weight))
+            self._bias_cache = {}
         return self._packed[1], self._packed[2]
 
-    def _bias(self, table: torch.Tensor, L: int, keys: int, n_valid: int) -> torch.Tensor:
-        """fp32 [heads, L, keys]: position bias of the first `keys` key positions, -3e38 on keys >= n_valid."""
-        dev = table.device
-        b = self._bucket_cache.get((L, str(dev)))
-        if b is None:
-            rel = (self.pos_embedding or self.blocks[0].pos_embedding).buckets(L, L)
-            b = self._bucket_cache[(L, str(dev))] = rel.to(dev)
-        bias = table.float()[b[:, :keys]].permute(2, 0, 1).contiguous()
-        if n_valid < keys:
-            bias[:, :, n_valid:] = _NEG
-        return bias
+    def _rel_bias(self, L: int) -> List[torch.Tensor]:
+        """Per block: fp32 [heads, 2L-1], the position bias of key j for query i at [h, (j - i) + L - 1]
+        (reference t5.py:229-263).  Derived from the bucket embeddings: cached with the packed weights."""
+        self._weights()
+        tabs = self._bias_cache.get(L)
+        if tabs is None:
+            emb = self.pos_embedding or self.blocks[0].pos_embedding
+            idx = self._bucket_cache.get(L)
+            if idx is None:
+                idx = self._bucket_cache[L] = emb.relative_buckets(L)
+
+            def table(e):
+                w = e.embedding.weight.detach()
+                return w.float()[idx.to(w.device)].t().contiguous()
+
+            if self.pos_embedding is not None:
+                tabs = [table(self.pos_embedding)] * len(self.blocks)
+            else:
+                tabs = [table(blk.pos_embedding) for blk in self.blocks]
+            self._bias_cache = {L: tabs}
+        return tabs
 
     @torch.no_grad()
-    def _encode_one(self, ids: torch.Tensor, n_valid: int) -> torch.Tensor:
+    def _encode(self, ids: torch.Tensor, k_lens: Optional[torch.Tensor]) -> torch.Tensor:
+        """ids [B, L] int64, k_lens int32 [B] on the same device (valid tokens per sample) or None -> bf16 [B, L, dim]."""
         layers, norm_w = self._weights()
-        L, d, da, nh, hd, eps = ids.shape[0], self.dim, self.dim_attn, self.num_heads, self.dim_attn // self.num_heads, 1e-6
+        B, L = ids.shape
+        d, da, nh, eps = self.dim, self.dim_attn, self.num_heads, 1e-6
+        hd = da // nh
         dev = ids.device
-        if L % 64 != 0:
-            raise NotImplementedError(f"sequence length {L} must be a multiple of 64 (the pipeline pads to text_len 512)")
-        keys = (n_valid + 63) // 64 * 64                    # key columns the score GEMMs cover; the rest is padding
-        x = self.token_embedding.weight.detach()[ids].to(bf16).contiguous()          # [L, d]
+        if hd not in (64, 128):
+            raise NotImplementedError(f"head_dim {hd}: ovb_attn_relbias_fwd has 64- and 128-wide heads (umT5-XXL: 64)")
+        rel_bias = self._rel_bias(L)
+        M = B * L
+        x = self.token_embedding.weight.detach()[ids.reshape(-1)].to(bf16).contiguous()          # [B*L, d]
         h = torch.empty_like(x)
-        qk = torch.empty((L, 2 * da), device=dev, dtype=bf16)
-        vt = torch.empty((da, keys), device=dev, dtype=bf16)
-        S = torch.empty((L, keys), device=dev, dtype=f32)
-        P = torch.empty((L, keys), device=dev, dtype=bf16)
-        att = torch.empty((L, da), device=dev, dtype=bf16)
-        zero = torch.zeros((L, self.dim_ffn), device=dev, dtype=f32)
-        shared = None if self.pos_embedding is None else self._bias(self.pos_embedding.embedding.weight.detach(), L, keys, n_valid)
-        for blk, W in zip(self.blocks, layers):
-            bias = shared if shared is not None else self._bias(blk.pos_embedding.embedding.weight.detach(), L, keys, n_valid)
+        qkv = torch.empty((M, 3 * da), device=dev, dtype=bf16)
+        att = torch.empty((M, da), device=dev, dtype=bf16)
+        zero = torch.zeros((M, self.dim_ffn), device=dev, dtype=f32)
+        u = torch.empty_like(zero)
+        q, k, v = (qkv[:, i * da:(i + 1) * da].unflatten(1, (nh, hd)).unflatten(0, (B, L)) for i in range(3))
+        for W, bias in zip(layers, rel_bias):
             # ---- self attention (no 1/sqrt(d) scaling in T5)
             h.copy_(x)
             ops.rmsnorm_rope_(h, W["n1"], eps)
-            ops.gemm(h, W["qk"], None, epilogue=EPI_BF16, out=qk)
-            ops.gemm(W["v"], h[:keys], None, epilogue=EPI_BF16, out=vt)                 # V^T [da, keys]
-            for i in range(nh):
-                cols = slice(i * hd, (i + 1) * hd)
-                S.copy_(bias[i])
-                ops.gemm(qk[:, cols], qk[:keys, da + i * hd:da + (i + 1) * hd], None, epilogue=EPI_RESID_F32,
-                         out=S, resid=S)                                                  # bias + q k^T
-                vae_ops.softmax_rows(S, 1.0, out=P)
-                ops.gemm(P, vt[cols], None, epilogue=EPI_BF16, out=att[:, cols])
+            ops.gemm(h, W["qkv"], None, epilogue=EPI_BF16, out=qkv)
+            ops.attention_relbias(q, k, v, bias, k_lens, 1.0, out=att.view(B, L, nh, hd))
             ops.gemm(att, W["o"], None, epilogue=EPI_RESID_BF16, out=x, resid=x)
             # ---- gated-GELU feed forward
             h.copy_(x)
             ops.rmsnorm_rope_(h, W["n2"], eps)
             g = ops.cast_bf16_to_f32(ops.gemm(h, W["gate"], None, epilogue=EPI_GELU_BF16))
-            u = ops.gemm(h, W["fc1"], None, epilogue=EPI_GATE_RESID_F32, out=torch.zeros_like(zero), resid=zero, gate=g)
+            ops.gemm(h, W["fc1"], None, epilogue=EPI_GATE_RESID_F32, out=u, resid=zero, gate=g)
             ops.gemm(ops.cast_f32_to_bf16(u), W["fc2"], None, epilogue=EPI_RESID_BF16, out=x, resid=x)
         ops.rmsnorm_rope_(x, norm_w, eps)
-        return x
+        return x.view(B, L, d)
 
     def forward(self, ids, mask=None):
         if ids.device.type != "cuda":
             raise RuntimeError("T5Encoder (B200 path) needs CUDA tensors; there is no CPU fallback")
-        outs = []
-        for b in range(ids.shape[0]):
-            n = ids.shape[1] if mask is None else int((mask[b] > 0).sum())
-            outs.append(self._encode_one(ids[b], max(n, 1)))
-        return torch.stack(outs)
+        # the tokenizer pads at the end (tokenizers.py:60-70): the mask is a prefix, its row sums are the key counts;
+        # they stay on the device (no host synchronisation)
+        k_lens = None if mask is None else mask.gt(0).sum(dim=1).clamp_(min=1).to(torch.int32).contiguous()
+        return self._encode(ids, k_lens)
 
 
 def clean_whitespace(text: str) -> str:

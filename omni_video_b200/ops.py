@@ -211,6 +211,41 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
     return out
 
 
+def attention_relbias(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rel_bias: torch.Tensor,
+                      k_lens: Optional[torch.Tensor] = None, softmax_scale: float = 1.0,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """umT5 self-attention, all heads and samples in one launch (reference t5.py:96-117).
+    q/k/v: bf16 [B, L, H, D] views (D = 64 or 128, heads packed per row); rel_bias: fp32 [H, 2L-1] with the bias of
+    key j for query i at [h, (j - i) + L - 1]; k_lens: int32 DEVICE tensor [B] (valid keys per sample) or None.
+    Returns bf16 [B, L, H, D]."""
+    _need_cuda(q, k, v, rel_bias, k_lens, out)
+    lib = _lib.load()
+    assert q.dim() == 4 and q.shape == k.shape == v.shape
+    B, L, H, D = q.shape
+    if D not in (64, 128):
+        raise ValueError(f"ovb_attn_relbias_fwd supports head_dim 64 or 128 (got {D})")
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        assert t.dtype == bf16, f"{n} must be bf16"
+        assert t.stride(3) == 1 and t.stride(2) == D, f"{n}: heads must be packed [H,{D}] per row"
+    assert rel_bias.dtype == f32 and rel_bias.shape == (H, 2 * L - 1) and rel_bias.stride(1) == 1
+    if k_lens is not None:
+        assert k_lens.dtype == torch.int32 and k_lens.shape == (B,) and k_lens.is_contiguous()
+    if out is None:
+        out = torch.empty((B, L, H, D), device=q.device, dtype=bf16)
+    assert out.dtype == bf16 and out.shape == (B, L, H, D) and out.stride(3) == 1 and out.stride(2) == D
+    args = _lib.AttnRelBiasArgs()
+    args.q, args.q_row_stride, args.q_batch_stride = q.data_ptr(), q.stride(1), q.stride(0)
+    args.k, args.k_row_stride, args.k_batch_stride = k.data_ptr(), k.stride(1), k.stride(0)
+    args.v, args.v_row_stride, args.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
+    args.out, args.o_row_stride, args.o_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    args.rel_bias, args.bias_head_stride = rel_bias.data_ptr(), rel_bias.stride(0)
+    args.k_lens = _ptr(k_lens)
+    args.B, args.H, args.L, args.head_dim = B, H, L, D
+    args.softmax_scale = float(softmax_scale)
+    _lib.check(lib.ovb_attn_relbias_fwd(C.byref(args), _stream()), "ovb_attn_relbias_fwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------- layernorm
 def layernorm_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, eps: float, *,
                        rows_per_sample: int = 0, out_dtype=bf16, round_ln_bf16: bool = False,

@@ -211,6 +211,55 @@ def test_attention_large_scores(ops):
     assert O.rel_l2(out.float().cpu(), ref.cpu()) < 1e-2
 
 
+def _relbias_ref(q, k, v, rel_bias, k_lens, scale):
+    """fp32 torch restatement of reference t5.py:101-112 with the bias given in (key - query) form; P is rounded to
+    bf16 before P V like the kernel (and like the reference's bf16 execution, t5.py:111)."""
+    B, L, H, D = q.shape
+    delta = (torch.arange(L)[None, :] - torch.arange(L)[:, None] + L - 1).to(q.device)
+    S = torch.einsum("bihc,bjhc->bhij", q.float(), k.float()) * scale + rel_bias[:, delta][None]
+    if k_lens is not None:
+        S = S.masked_fill(torch.arange(L, device=q.device)[None, None, None, :] >= k_lens.view(B, 1, 1, 1).long(), float("-inf"))
+    P = torch.softmax(S, dim=-1).to(bf16).float()
+    return torch.einsum("bhij,bjhc->bihc", P, v.float())
+
+
+@pytest.mark.parametrize("B,L,H,D,k_lens,scale", [
+    (1, 64, 2, 64, None, 1.0),              # one tile
+    (2, 512, 64, 64, [77, 512], 1.0),       # the umT5-XXL launch: 64 heads of 64, ragged batch
+    (3, 200, 3, 64, [1, 130, 200], 1.0),    # L not a multiple of the 64-row tiles, a single valid key
+    (2, 130, 2, 128, [130, 65], 0.5),       # 128-wide heads, scaled scores
+])
+def test_attention_relbias_vs_fp32(ops, B, L, H, D, k_lens, scale):
+    """ovb_attn_relbias_fwd (umT5 self-attention, all heads in one launch) on column blocks of a fused QKV buffer."""
+    rng = _rng(11 + L)
+    qkv = _randn(rng, B, L, 3, H, D).to(bf16).cuda()
+    qkv[:, :, 0] *= 0.35                                           # unscaled T5 scores: keep the softmax from saturating
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    rel_bias = _randn(rng, H, 2 * L - 1, scale=0.7).cuda()
+    kl = None if k_lens is None else torch.tensor(k_lens, dtype=torch.int32, device="cuda")
+    out = ops.attention_relbias(q, k, v, rel_bias, kl, scale)
+    ref = _relbias_ref(q, k, v, rel_bias, kl, scale)
+    assert out.shape == (B, L, H, D) and out.dtype == bf16 and bool(torch.isfinite(out.float()).all())
+    for b in range(B):                                             # per sample, so a wrong key count cannot hide
+        err = O.rel_l2(out[b].float().cpu(), ref[b].cpu())
+        assert err < 6e-3, (b, err)
+    # rows are independent of the launch shape: one sample alone gives the same bits as inside the batch
+    if B > 1:
+        alone = ops.attention_relbias(q[1:2], k[1:2], v[1:2], rel_bias, None if kl is None else kl[1:2].contiguous(), scale)
+        assert torch.equal(alone[0], out[1])
+
+
+def test_attention_relbias_rejects_bad_arguments(ops):
+    q = torch.zeros(1, 64, 2, 32, dtype=bf16, device="cuda")
+    with pytest.raises(ValueError):
+        ops.attention_relbias(q, q, q, torch.zeros(2, 127, device="cuda"))
+    from omni_video_b200 import _lib
+    import ctypes as C
+    a = _lib.AttnRelBiasArgs()
+    assert _lib.load().ovb_attn_relbias_fwd(C.byref(a), None) == -1          # null pointers
+    assert b"null pointer" in _lib.load().ovb_last_error()
+
+
 # ----------------------------------------------------------------------------------- elementwise
 @pytest.mark.parametrize("rows,d,rps", [(64, 256, 32), (100, 1536, 50), (33, 5120, 33)])
 def test_layernorm_modulate(ops, rows, d, rps):

@@ -32,7 +32,7 @@ def test_t5_encoder_vs_oracle(shared_pos, lengths, seq_len):
 def test_t5_encoder_at_umt5_xxl_width_vs_oracle():
     """One block at the REAL umT5-XXL width (reference t5.py:467-476: dim 4096, 64 heads of 64, ffn 10240, 32
     buckets, per-layer position bias) on a 512-token prompt batch (77 and 512 valid tokens): every GEMM shape, the
-    64-head score/softmax/PV loop and the padding-key mask at the size the pipeline runs.  The depth (24 blocks)
+    64-head attention launch and the padding-key mask at the size the pipeline runs.  The depth (24 blocks)
     repeats this block; the vocabulary only sizes an embedding lookup and is cut to 512 rows."""
     from omni_video_b200.modules.t5 import T5Encoder
     cfg = dict(vocab=512, dim=4096, dim_attn=4096, dim_ffn=10240, num_heads=64, num_layers=1, num_buckets=32,
@@ -53,3 +53,95 @@ def test_t5_encoder_at_umt5_xxl_width_vs_oracle():
         # at the real width the averaging over 4096 channels brings the bf16 error under the north-star bound
         # (measured 8.4e-3 / 9.0e-3); the toy cases above keep 2.5e-2 (dim 128, sharp unscaled softmaxes)
         assert bool(torch.isfinite(out[b, :n].float()).all()) and err <= 1e-2
+
+
+def _reference_bf16_execution(sd, cfg, ids, mask):
+    """How the REFERENCE itself computes in bf16 (T5EncoderModel runs `dtype=torch.bfloat16`, t5.py:478-492): every
+    nn.Linear and einsum returns bf16, T5LayerNorm casts to bf16 before the weight (:61-63), the softmax runs in fp32
+    and is cast back (:111), residual adds are bf16 (:169-170).  Test infrastructure: the yardstick for how far a bf16
+    execution of 24 blocks may drift from the fp32 oracle."""
+    b16 = torch.bfloat16
+    w = {k: v.to(b16) for k, v in sd.items()}
+    L, nh = ids.shape[1], cfg["num_heads"]
+    buckets = T.relative_position_bucket(L, L, cfg["num_buckets"])
+
+    def norm(x, g):
+        return g * (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)).to(b16)
+
+    outs = []
+    for b in range(ids.shape[0]):
+        x = w["token_embedding.weight"][ids[b]]
+        for i in range(cfg["num_layers"]):
+            p = f"blocks.{i}."
+            h = norm(x, w[p + "norm1.weight"])
+            q, k, v = ((h @ w[p + f"attn.{n}.weight"].T).view(L, nh, -1) for n in "qkv")
+            bias = w[p + "pos_embedding.embedding.weight"][buckets].permute(2, 0, 1).clone()
+            bias = bias.masked_fill(mask[b].view(1, 1, L) == 0, torch.finfo(b16).min)
+            a = torch.softmax((torch.einsum("inc,jnc->nij", q, k) + bias).float(), dim=-1).to(b16)
+            x = x + torch.einsum("nij,jnc->inc", a, v).reshape(L, -1) @ w[p + "attn.o.weight"].T
+            h = norm(x, w[p + "norm2.weight"])
+            g = torch.nn.functional.gelu(h @ w[p + "ffn.gate.0.weight"].T, approximate="tanh")
+            x = x + ((h @ w[p + "ffn.fc1.weight"].T) * g) @ w[p + "ffn.fc2.weight"].T
+        outs.append(norm(x, w["norm.weight"])[:int((mask[b] > 0).sum())])
+    return outs
+
+
+@pytest.mark.parametrize("q_gain", [4.0, 1.0])
+def test_t5_encoder_umt5_xxl_full_depth(q_gain):
+    """The whole umT5-XXL encoder at its real size (reference t5.py:455-468: 24 blocks, dim 4096, 64 heads, ffn 10240;
+    4.7 G random-init parameters generated on the device, vocabulary cut to 512 rows) on the pipeline's prompt batch
+    (2 x 512 tokens, 77 and 512 valid).  The checker is the oracle's arithmetic (oracle/t5.py) evaluated in fp32 on
+    the same device tensors, because the fp32 state (19 GB) makes a CPU run of it a matter of minutes.  24 blocks of
+    bf16 arithmetic through unscaled softmaxes drift from fp32 whoever executes them: the bound is the drift of the
+    reference's own bf16 execution (`_reference_bf16_execution`) on the same weights.  q_gain 4 is oracle/synth.py's
+    scale of the query projection (score std ~4: sharp softmaxes, the drift is chaotic), q_gain 1 gives scores of unit
+    variance.  Also counts launches: 10 per block, whatever the head count."""
+    from omni_video_b200 import _lib
+    from omni_video_b200.modules.t5 import T5Encoder
+    cfg = dict(vocab=512, dim=4096, dim_attn=4096, dim_ffn=10240, num_heads=64, num_layers=24, num_buckets=32,
+               shared_pos=False)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gen = torch.Generator(device="cuda").manual_seed(1818)
+    shapes = synth.t5_state_dict(dict(cfg, vocab=2, dim=128, dim_attn=128, dim_ffn=128, num_heads=2, num_layers=24))
+    d, da, df, nh = cfg["dim"], cfg["dim_attn"], cfg["dim_ffn"], cfg["num_heads"]
+    scale = {"attn.q.weight": ((da, d), (d * (da // nh)) ** -0.5 * q_gain), "attn.k.weight": ((da, d), d ** -0.5),
+             "attn.v.weight": ((da, d), d ** -0.5), "attn.o.weight": ((d, da), da ** -0.5),
+             "ffn.gate.0.weight": ((df, d), d ** -0.5), "ffn.fc1.weight": ((df, d), d ** -0.5),
+             "ffn.fc2.weight": ((d, df), df ** -0.5), "pos_embedding.embedding.weight": ((32, nh), 0.5)}
+    sd = {}
+    for name in shapes:                                  # the reference's parameter names, synth's init scales
+        tail = name.split(".", 2)[2] if name.startswith("blocks.") else name
+        if tail in scale:
+            shp, sc = scale[tail]
+            w = torch.randn(shp, generator=gen, device="cuda") * sc
+        elif name == "token_embedding.weight":
+            w = torch.randn((cfg["vocab"], d), generator=gen, device="cuda")
+        else:                                            # norm weights around 1
+            w = 1.0 + 0.05 * torch.randn((d,), generator=gen, device="cuda")
+        sd[name] = w.bfloat16().float()                  # bf16-representable fp32, as synth.round_bf16 does
+    with torch.device("cuda"):
+        m = T5Encoder(**cfg)
+    m = m.to(torch.bfloat16).eval().requires_grad_(False)
+    m.load_state_dict({k: v.bfloat16() for k, v in sd.items()}, strict=True)
+    lengths, seq_len = [77, 512], 512
+    ids, mask = synth.t5_inputs(cfg, lengths, seq_len, seed=7)
+    ids, mask = ids.cuda(), mask.cuda()
+    m(ids, mask)                                         # packs the weights, builds the bias tables
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    out = m(ids, mask)
+    t1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - n0
+    want = T.t5_encode(sd, cfg, ids, mask)
+    ref16 = _reference_bf16_execution(sd, cfg, ids, mask)
+    assert out.shape == (2, seq_len, 4096) and out.dtype == torch.bfloat16
+    assert launches == 24 * 10 + 1, launches
+    for b, n in enumerate(lengths):
+        err = O.rel_l2(out[b, :n].float().cpu(), want[b].cpu())
+        err_ref = O.rel_l2(ref16[b].float().cpu(), want[b].cpu())
+        print(f"umT5-XXL 24 blocks (q_gain {q_gain:g}), {n} tokens: rel-L2 vs fp32 oracle arithmetic {err:.3e} (the reference's own bf16 "
+              f"execution: {err_ref:.3e}); {launches} launches, {t0.elapsed_time(t1):.2f} ms for the 2 x 512 batch")
+        assert bool(torch.isfinite(out[b, :n].float()).all()) and err <= 1.25 * err_ref + 5e-3
