@@ -130,43 +130,46 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One WARP per row, the row held in registers (VPL 16-byte vectors per lane, lane i owns vectors
-// i, i+32, ...: every warp-wide access is one contiguous 512 B / 1 KB run).  No shared memory and
-// no __syncthreads: the two reductions are five shuffles each, and 8 independent rows are in
-// flight per CTA.  (The one-CTA-per-row form below spends most of its time in the two block
-// barriers: 0.59 / 0.36 of copy bandwidth for LayerNorm / RMSNorm at d = 1536.)
+// One WARP per row, the row held in registers (VPL float4 vectors per lane, lane l owns vectors
+// l, l+32, ...: every warp-wide load is one contiguous 512-byte run).  No shared memory and no
+// __syncthreads: the two reductions are five shuffles each.  The launch is persistent: one grid-stride
+// pass of sm_count x resident CTAs (two per SM up to d = 2048), which is what lifted d = 5120 from 0.55
+// to 0.63 of copy bandwidth.  At d = 1536 the kernel sits at 0.75-0.77 whatever the occupancy (two,
+// three or four CTAs per SM and either vector layout were measured within 3 %: scripts/norm_time.py).
+// (The one-CTA-per-row form above spends most of its time in the two block barriers: 0.59 / 0.36 of copy
+// bandwidth for LayerNorm / RMSNorm at d = 1536.)
+__device__ __forceinline__ float4 load4_bf16(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+
 template <int VPL>
-__global__ void __launch_bounds__(256) layernorm_warp_kernel(const LnParams p) {
+__global__ void __launch_bounds__(256, VPL <= 16 ? 2 : 1) layernorm_warp_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * 8;
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += warps) {
-    float v[VPL][8];
+    float4 v[VPL];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int c0 = (i * 32 + lane) * 8;
+      const int c0 = (i * 32 + lane) * 4;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c0 < p.d) {
         if (p.x_is_bf16)
-          load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx + c0, v[i]);
+          v[i] = load4_bf16(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx + c0);
         else
-          load8_f32(reinterpret_cast<const float*>(p.x) + row * p.ldx + c0, v[i]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+          v[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + row * p.ldx + c0);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
     const float mean = warp_sum(s) / p.d;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if ((i * 32 + lane) * 8 < p.d) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float t = v[i][j] - mean;
-          q += t * t;
-        }
+      if ((i * 32 + lane) * 4 < p.d) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
       }
     }
     const float rstd = rsqrtf(warp_sum(q) / p.d + p.eps);
@@ -174,31 +177,28 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(const LnParams p) {
     const long long mod_off = sample * p.mod_sample_stride + (row - sample * p.rows_per_sample) * p.mod_row_stride;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int c0 = (i * 32 + lane) * 8;
+      const int c0 = (i * 32 + lane) * 4;
       if (c0 >= p.d) continue;
-      float y[8];
+      float y[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+      if (p.round_ln_bf16) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        y[j] = (v[i][j] - mean) * rstd;
-        if (p.round_ln_bf16) y[j] = bf16_round(y[j]);
+        for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j]);
       }
+      float4 a, b;
       if (p.mode == OVB_LN_MODULATE) {
-        float sc[8], sh[8];
-        load8_f32(reinterpret_cast<const float*>(p.a) + mod_off + c0, sc);
-        load8_f32(reinterpret_cast<const float*>(p.b) + mod_off + c0, sh);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = y[j] * (1.0f + sc[j]) + sh[j];
+        a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.a) + mod_off + c0);
+        b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.b) + mod_off + c0);
+        a.x += 1.0f; a.y += 1.0f; a.z += 1.0f; a.w += 1.0f;
       } else {
-        float w[8], bb[8];
-        load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.a) + c0, w);
-        load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.b) + c0, bb);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = y[j] * w[j] + bb[j];
+        a = load4_bf16(reinterpret_cast<const __nv_bfloat16*>(p.a) + c0);
+        b = load4_bf16(reinterpret_cast<const __nv_bfloat16*>(p.b) + c0);
       }
+      y[0] = y[0] * a.x + b.x; y[1] = y[1] * a.y + b.y; y[2] = y[2] * a.z + b.z; y[3] = y[3] * a.w + b.w;
       if (p.out_is_f32)
-        store8_f32(reinterpret_cast<float*>(p.out) + row * p.ldo + c0, y);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + c0) = make_float4(y[0], y[1], y[2], y[3]);
       else
-        store8_bf16(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + c0, y);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + c0) =
+            make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
     }
   }
 }
@@ -275,22 +275,24 @@ __global__ void rmsnorm_rope_kernel(const RmsRopeParams p) {
 //     bf16 values is exact in fp32, so its bf16 rounding is the reference's (`.type_as(x) * weight`);
 //   * a lane's vectors all sit at the same offset inside a head (vector stride 32 lanes x 8 = 256
 //     columns = 2 heads), so its four (cos, sin) pairs are fetched ONCE per row, not per vector.
-template <int VPL>
-__global__ void __launch_bounds__(256) rmsnorm_rope_warp_kernel(const RmsRopeParams p) {
+//   * registers are bounded for three resident CTAs per SM up to d = 1536 (32-bit element offsets; the
+//     per-vector destination pointers exist only in the SCATTER instantiation).
+template <int VPL, bool SCATTER>
+__global__ void __launch_bounds__(256, VPL <= 6 ? 3 : 1) rmsnorm_rope_warp_kernel(const RmsRopeParams p) {
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * 8;
   const int hw = p.H * p.W;
   const int n_tok = p.F * hw;
   const int pair0 = (lane & 15) * 4;  // ((i*32 + lane) * 8 & 127) / 2 for every i
   // element offset of each of this lane's vectors inside a row (column-split layout): row-invariant
-  long long off[VPL];
-  __nv_bfloat16* dbase[VPL];  // scatter form: destination of this vector at row 0 (maybe peer memory)
+  int off[VPL];               // fits 32 bits: the host checks (col_split - 1) * col_split_stride + d < 2^31
+  __nv_bfloat16* dbase[SCATTER ? VPL : 1];  // scatter form: destination of this vector at row 0 (maybe peer memory)
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c0 = (i * 32 + lane) * 8;
     const int seg = c0 / p.cols_per_split;
-    off[i] = seg * p.col_split_stride + (c0 - seg * p.cols_per_split);
-    dbase[i] = (p.scatter && c0 < p.d) ? p.dst[seg] + (c0 - seg * p.cols_per_split) : nullptr;
+    off[i] = static_cast<int>(seg * p.col_split_stride) + (c0 - seg * p.cols_per_split);
+    if (SCATTER) dbase[i] = c0 < p.d ? p.dst[seg] + (c0 - seg * p.cols_per_split) : nullptr;
   }
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += warps) {
     uint4 raw[VPL];
@@ -309,10 +311,10 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_warp_kernel(const RmsRopePar
         q = fmaf(hi, hi, q);
       }
     }
-    if (p.copy_only) {  // plain scatter of the row (V): no statistics, no rounding
+    if (SCATTER && p.copy_only) {  // plain scatter of the row (V): no statistics, no rounding
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
-        if ((i * 32 + lane) * 8 < p.d) *reinterpret_cast<uint4*>(dbase[i] + row * p.dst_ld) = raw[i];
+        if ((i * 32 + lane) * 8 < p.d) *reinterpret_cast<uint4*>(dbase[SCATTER ? i : 0] + row * p.dst_ld) = raw[i];
       continue;
     }
     const float rinv = rsqrtf(warp_sum(q) / p.d + p.eps);
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_warp_kernel(const RmsRopePar
         }
         o[j] = y;
       }
-      __nv_bfloat16* dptr = p.scatter ? dbase[i] + row * p.dst_ld : xrow + off[i];
+      __nv_bfloat16* dptr = SCATTER ? dbase[SCATTER ? i : 0] + row * p.dst_ld : xrow + off[i];
       *reinterpret_cast<uint4*>(dptr) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
@@ -549,10 +551,20 @@ __global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ mod,
 
 using namespace ovb;
 
-// grid for the warp-per-row kernels: 8 rows per CTA pass, at most 8 resident CTAs' worth per SM
-static inline int warp_row_grid(int rows) {
+// grid for the warp-per-row kernels: 8 rows per CTA pass; persistent at sm_count x the CTAs of this kernel that
+// fit one SM (occ: per-device cache of the occupancy query, owned by the call site of each instantiation)
+template <typename K>
+static inline int warp_row_grid(int rows, K kernel, int (&occ)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev < 0 || dev >= 64 ? 0 : dev;
+  if (occ[dev] == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+    occ[dev] = nb;
+  }
   const long long ctas = (static_cast<long long>(rows) + 7) / 8;
-  const long long cap = 148LL * 8;
+  const long long cap = static_cast<long long>(device_sm_count()) * occ[dev];
   return static_cast<int>(ctas < cap ? ctas : cap);
 }
 
@@ -582,17 +594,22 @@ extern "C" int ovb_layernorm(const ovb_ln_args* a, void* stream) {
   p.mod_row_stride = a->mod_row_stride; p.mod_sample_stride = a->mod_sample_stride;
   p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : a->rows;
   p.round_ln_bf16 = a->round_ln_bf16;
-  const int vpl = (a->d / 8 + 31) / 32;  // 16-byte vectors per lane with one warp per row
-  const int wgrid = warp_row_grid(a->rows);
+  const int vpl = (a->d / 4 + 31) / 32;  // float4 vectors per lane with one warp per row
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (vpl <= 1) layernorm_warp_kernel<1><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 2) layernorm_warp_kernel<2><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 4) layernorm_warp_kernel<4><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 6) layernorm_warp_kernel<6><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 8) layernorm_warp_kernel<8><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 12) layernorm_warp_kernel<12><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 16) layernorm_warp_kernel<16><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 20) layernorm_warp_kernel<20><<<wgrid, 256, 0, st>>>(p);
+#define OVB_LN_LAUNCH(V)                                                                           \
+  do {                                                                                             \
+    static int occ[64] = {};                                                                       \
+    layernorm_warp_kernel<V><<<warp_row_grid(a->rows, layernorm_warp_kernel<V>, occ), 256, 0, st>>>(p); \
+  } while (0)
+  if (vpl <= 2) OVB_LN_LAUNCH(2);
+  else if (vpl <= 4) OVB_LN_LAUNCH(4);
+  else if (vpl <= 8) OVB_LN_LAUNCH(8);
+  else if (vpl <= 12) OVB_LN_LAUNCH(12);
+  else if (vpl <= 16) OVB_LN_LAUNCH(16);
+  else if (vpl <= 24) OVB_LN_LAUNCH(24);
+  else if (vpl <= 32) OVB_LN_LAUNCH(32);
+  else if (vpl <= 40) OVB_LN_LAUNCH(40);
+#undef OVB_LN_LAUNCH
   else {  // d > 5120: the row no longer fits one warp's registers in fp32
     const int threads = ((a->d / 8 + 31) / 32) * 32;
     layernorm_kernel<<<a->rows, threads, 0, st>>>(p);
@@ -646,15 +663,25 @@ extern "C" int ovb_rmsnorm_rope(const ovb_rmsnorm_rope_args* a, void* stream) {
     OVB_CHECK_ARG(!a->copy_only, "ovb_rmsnorm_rope: copy_only needs dst_ptrs");
   }
   const int vpl = (a->d / 8 + 31) / 32;
-  const int wgrid = warp_row_grid(a->rows);
+  OVB_CHECK_ARG(static_cast<long long>(col_split - 1) * a->col_split_stride + a->d < (1LL << 31),
+                "ovb_rmsnorm_rope: column-split layout spans more than 2^31 elements");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (vpl <= 1) rmsnorm_rope_warp_kernel<1><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 2) rmsnorm_rope_warp_kernel<2><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 4) rmsnorm_rope_warp_kernel<4><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 6) rmsnorm_rope_warp_kernel<6><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 8) rmsnorm_rope_warp_kernel<8><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 16) rmsnorm_rope_warp_kernel<16><<<wgrid, 256, 0, st>>>(p);
-  else if (vpl <= 20) rmsnorm_rope_warp_kernel<20><<<wgrid, 256, 0, st>>>(p);
+#define OVB_RMS_LAUNCH(V)                                                                                        \
+  do {                                                                                                           \
+    static int occ0[64] = {}, occ1[64] = {};                                                                     \
+    if (p.scatter)                                                                                               \
+      rmsnorm_rope_warp_kernel<V, true><<<warp_row_grid(a->rows, rmsnorm_rope_warp_kernel<V, true>, occ1), 256, 0, st>>>(p);  \
+    else                                                                                                         \
+      rmsnorm_rope_warp_kernel<V, false><<<warp_row_grid(a->rows, rmsnorm_rope_warp_kernel<V, false>, occ0), 256, 0, st>>>(p); \
+  } while (0)
+  if (vpl <= 1) OVB_RMS_LAUNCH(1);
+  else if (vpl <= 2) OVB_RMS_LAUNCH(2);
+  else if (vpl <= 4) OVB_RMS_LAUNCH(4);
+  else if (vpl <= 6) OVB_RMS_LAUNCH(6);
+  else if (vpl <= 8) OVB_RMS_LAUNCH(8);
+  else if (vpl <= 16) OVB_RMS_LAUNCH(16);
+  else if (vpl <= 20) OVB_RMS_LAUNCH(20);
+#undef OVB_RMS_LAUNCH
   else {  // d > 5120
     const int threads = ((a->d / 8 + 31) / 32) * 32;
     rmsnorm_rope_kernel<<<a->rows, threads, 0, st>>>(p);
