@@ -329,6 +329,40 @@ def test_rmsnorm_rope(ops, grid, H, pad, offset):
     assert (d2 > 0).float().mean().item() < 1e-3
 
 
+def test_scatter_forms_on_one_gpu_match_the_plain_forms(ops):
+    """The sequence-parallel scatter forms (include/ovb200.h: `dst_ptrs` of ovb_rmsnorm_rope, `out_ptrs` of
+    ovb_attn_fwd) write through raw destination pointers — peer-mapped memory under Ulysses.  With local buffers
+    as destinations they must give the bits of the plain forms: this keeps the scatter instantiations covered on
+    a one-GPU box (the multi-GPU checks are scripts/sp_check.py and the `parity` object of bench.py)."""
+    rng = _rng(21)
+    rows, groups, dc = 700, 2, 256                                   # d = 512: 4 heads, 2 per column group
+    x = _randn(rng, groups, rows, dc).to(bf16).cuda()
+    w = (1 + 0.1 * _randn(rng, groups * dc)).to(bf16).cuda()
+    cs = ops.rope_cos_sin_table().cuda()
+    kw = dict(cs_table=cs, grid=(7, 10, 10), rows_per_sample=rows)
+    want = ops.rmsnorm_rope_(x.clone(), w, 1e-6, **kw)
+    ld = dc + 8
+    dst = [torch.full((rows + 3, ld), 7.0, dtype=bf16, device="cuda") for _ in range(groups)]
+    src = x.clone()
+    ops.rmsnorm_rope_(src, w, 1e-6, dst_ptrs=[t.data_ptr() for t in dst], dst_ld=ld, **kw)
+    assert torch.equal(src, x)                                       # the scatter form leaves its input alone
+    for g in range(groups):
+        assert torch.equal(dst[g][:rows, :dc], want[g])
+        assert bool((dst[g][rows:] == 7.0).all()) and bool((dst[g][:, dc:] == 7.0).all())      # nothing else touched
+    ops.rmsnorm_rope_(src, w, 1e-6, dst_ptrs=[t.data_ptr() for t in dst], dst_ld=ld, copy_only=True)
+    for g in range(groups):
+        assert torch.equal(dst[g][:rows, :dc], x[g])
+
+    L, H, per = 600, 2, 300
+    q, k, v = (_randn(rng, 1, L, H, 128).to(bf16).cuda() for _ in range(3))
+    whole = ops.attention(q, k, v, k_lens=[555])
+    parts = [torch.zeros(per, H * 128 + 64, dtype=bf16, device="cuda") for _ in range(L // per)]
+    assert ops.attention(q, k, v, k_lens=[555], out_ptrs=[t.data_ptr() for t in parts], rows_per_out=per,
+                         out_row_stride=parts[0].stride(0)) is None
+    for i, t in enumerate(parts):
+        assert torch.equal(t[:, :H * 128].view(per, H, 128), whole[0, i * per:(i + 1) * per])
+
+
 def test_patchify_unpatchify(ops):
     rng = _rng(9)
     u = _randn(rng, 16, 3, 8, 12)
