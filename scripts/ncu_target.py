@@ -1,5 +1,5 @@
 """Small single-kernel targets for `ncu --set full` captures.
-    python scripts/ncu_target.py attn|attn_b2|gemm|gemm_resid|conv96|conv96_dual|conv192|head|norm|ln|rope
+    python scripts/ncu_target.py attn|attn_b2|gemm|gemm_resid|conv96|conv96_dual|conv192|head|norm|ln|rope|t5attn
 """
 import math
 import os
@@ -66,6 +66,14 @@ elif what == "ln":
     tbl = torch.randn(2, 6, d, device="cuda")
     o = torch.empty(L, d, device="cuda", dtype=bf16)
     fn = lambda: ops.layernorm_modulate(x, tbl[:, 1], tbl[:, 0], 1e-6, rows_per_sample=32760, out=o)  # noqa: E731
+elif what == "t5attn":
+    # umT5-XXL self-attention of the pipeline's prompt batch: 2 x 512 tokens, 64 heads of 64, one launch
+    B, L, H, D = 2, 512, 64, 64
+    qkv = torch.randn(B, L, 3, H, D, device="cuda").to(bf16)
+    rb = torch.randn(H, 2 * L - 1, device="cuda")
+    kl = torch.tensor([77, 512], dtype=torch.int32, device="cuda")
+    o = torch.empty(B, L, H, D, device="cuda", dtype=bf16)
+    fn = lambda: ops.attention_relbias(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], rb, kl, 1.0, out=o)  # noqa: E731
 elif what == "rope":
     L, d = 65520, 1536
     qkv = torch.randn(L, 3 * d, device="cuda").to(bf16)
