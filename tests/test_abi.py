@@ -118,6 +118,17 @@ def test_argument_errors_are_reported_before_any_launch():
     a.q_row_stride = a.k_row_stride = a.v_row_stride = a.o_row_stride = 130   # not a multiple of 8
     assert lib.ovb_attn_fwd(C.byref(a), None) < 0 and "strides" in err()
 
+    t = _lib.AttnRelBiasArgs()
+    t.q = t.k = t.v = t.out = t.rel_bias = 0x1000
+    t.B, t.H, t.L, t.head_dim = 1, 2, 64, 32                            # no 32-wide heads
+    assert lib.ovb_attn_relbias_fwd(C.byref(t), None) < 0 and "head_dim" in err()
+    t.head_dim = 64
+    t.q_row_stride = t.k_row_stride = t.v_row_stride = t.o_row_stride = 120      # rows narrower than H * head_dim
+    assert lib.ovb_attn_relbias_fwd(C.byref(t), None) < 0 and "row pitch" in err()
+    t.q_row_stride = t.k_row_stride = t.v_row_stride = t.o_row_stride = 128
+    t.bias_head_stride = 100                                            # table shorter than 2L - 1
+    assert lib.ovb_attn_relbias_fwd(C.byref(t), None) < 0 and "2L-1" in err()
+
     r = _lib.RmsRopeArgs()
     r.x = r.weight = 0x1000
     r.rows, r.d, r.ldx = 4, 100, 104                                   # d not a multiple of 8
