@@ -63,10 +63,13 @@ def back_to_back(fn, n=20):
 # Per-rank shapes of the sequence-parallel layouts (1.3B, 32760 tokens): M = 8190 rows at 8 GPUs (ulysses4 x cfg2),
 # 16380 at 4.  `GEMM_RANK_SHAPES=1 python scripts/gemm_time.py`
 if os.environ.get("GEMM_RANK_SHAPES"):
-    for M in (8190, 16380, 32760):
+    only = os.environ.get("GEMM_EPI", "").split(",") if os.environ.get("GEMM_EPI") else None
+    for M in (8190, 16380, 32760) + ((65520,) if only else ()):
         tot_ms, tot_fl = 0.0, 0.0
         for name, N, K, epi in [("qkv", 4608, 1536, "bf16"), ("o", 1536, 1536, "gate"), ("cross q", 1536, 1536, "bf16"),
                                 ("cross o", 1536, 1536, "resid"), ("ffn1", 8960, 1536, "gelu"), ("ffn2", 1536, 8960, "gate")]:
+            if only and epi not in only:
+                continue
             a = torch.randn(M, K, device="cuda").to(bf16)
             w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(bf16)
             b = torch.randn(N, device="cuda").to(bf16)
@@ -80,7 +83,7 @@ if os.environ.get("GEMM_RANK_SHAPES"):
                                            rows_per_sample=M)}[epi]
             ms = back_to_back(fn)
             wt = w.t()
-            ms_lib = back_to_back(lambda: torch.matmul(a, wt, out=o))
+            ms_lib = ms if only else back_to_back(lambda: torch.matmul(a, wt, out=o))
             fl = 2.0 * M * N * K
             tot_ms += ms
             tot_fl += fl
