@@ -52,21 +52,82 @@ _STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
 # ------------------------------------------------------------------------------------------------
 # Parameter containers with the reference's names (vae2_1.py:16-471)
 # ------------------------------------------------------------------------------------------------
-class CausalConv3d(nn.Conv3d):
-    """reference :16-35 — parameters only; the arithmetic is VAEEngine's."""
+def _leaf_device_check(x: torch.Tensor, what: str):
+    if x.device.type != "cuda":
+        raise RuntimeError(f"{what} (B200 path) needs CUDA tensors; there is no CPU fallback")
 
-    def forward(self, x, cache_x=None):  # pragma: no cover
-        raise NotImplementedError("use Wan2_1_VAE.encode/decode (VAEEngine); leaf modules only hold parameters")
+
+def _unit_affine(c: int, dev):
+    return torch.ones(c, device=dev, dtype=f32), torch.zeros(c, device=dev, dtype=f32)
+
+
+class CausalConv3d(nn.Conv3d):
+    """reference :16-35.  Inside `Wan2_1_VAE.encode/decode` the arithmetic is VAEEngine's (fused norms, strips,
+    resident channels-last activations); `forward` below is the same kernel at LEAF granularity, for callers that
+    drive the reference's module tree themselves: planar [B, C, T, H, W] in and out like the reference, one
+    ovb_planar_to_cl + ovb_conv3d (fp32 planar output mode) per sample."""
+
+    def _packed(self, causal_pad: int):
+        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else self.bias._version,
+               causal_pad)
+        if getattr(self, "_pack_key", None) != key:
+            _, ph, pw = self.padding
+            self._pack = vae_ops.pack_conv3d(self.weight, self.bias, causal_pad=causal_pad, stride=self.stride,
+                                             spatial_pad=(ph, pw))
+            self._pack_key = key
+        return self._pack
+
+    @torch.no_grad()
+    def forward(self, x, cache_x=None):
+        _leaf_device_check(x, "CausalConv3d")
+        kt, kh, kw = self.kernel_size
+        st, sh, sw = self.stride
+        pt, ph, pw = self.padding
+        cp = 2 * pt                                      # all of the time padding goes in front (:23-24)
+        if cache_x is not None and cp > 0:               # :29-32: cached frames replace part of the zero padding
+            x = torch.cat([cache_x.to(x.device), x], dim=2)
+            cp -= cache_x.shape[2]
+        if cp < 0:
+            raise ValueError(f"cache_x holds {cache_x.shape[2]} frames, more than the causal padding {2 * pt}")
+        B, Ci, Ti, H, W = x.shape
+        To, Ho, Wo = (Ti + cp - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+        pc = self._packed(cp)
+        one, zero = _unit_affine(Ci, x.device)
+        out = torch.empty((B, self.out_channels, To, Ho, Wo), device=x.device, dtype=f32)
+        for b in range(B):
+            xc = vae_ops.planar_to_cl(x[b].to(f32).contiguous(), one, zero, pc.cin)
+            vae_ops.conv3d(xc, pc, (To, Ho, Wo), out=out[b], out_strides=(Ho * Wo, Wo, 1),
+                           out_mode=vae_ops.CONV_OUT_F32_PLANAR, plane_stride=To * Ho * Wo)
+        return out.to(x.dtype)
 
 
 class RMS_norm(nn.Module):
-    """reference :38-53"""
+    """reference :38-53; `forward` = ovb_rmsnorm_silu_cl (without the SiLU) at leaf granularity, see CausalConv3d."""
 
     def __init__(self, dim, channel_first=True, images=True, bias=False):
         super().__init__()
         shape = (dim, 1, 1) if images else (dim, 1, 1, 1)
         self.gamma = nn.Parameter(torch.ones(shape if channel_first else (dim,)))
         self.scale = dim ** 0.5
+        self.channel_first = channel_first
+
+    @torch.no_grad()
+    def forward(self, x):
+        _leaf_device_check(x, "RMS_norm")
+        gamma = self.gamma.detach().reshape(-1).to(f32).contiguous()
+        c = gamma.numel()
+        if c % 16 != 0:
+            raise NotImplementedError(f"RMS_norm over {c} channels: the kernel takes multiples of 16")
+        if not self.channel_first:                       # [..., C]
+            return vae_ops.rmsnorm_silu(x.to(bf16).contiguous(), gamma, silu=False).to(x.dtype)
+        one, zero = _unit_affine(c, x.device)
+        lead = x.shape[0]
+        x4 = x.reshape((lead, c, -1) + tuple(x.shape[-2:]))                # [B, C, T | 1, H, W]
+        outs = []
+        for b in range(lead):
+            xc = vae_ops.planar_to_cl(x4[b].to(f32).contiguous(), one, zero, c)
+            outs.append(vae_ops.cl_to_planar(vae_ops.rmsnorm_silu(xc, gamma, silu=False), one, zero, c))
+        return torch.stack(outs).reshape(x.shape).to(x.dtype)
 
 
 class Resample(nn.Module):

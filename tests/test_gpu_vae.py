@@ -242,6 +242,36 @@ def test_head_conv_as_tap_planes_and_tap_sum(vops, T, H, W, pad):
     assert rel <= 3e-3
 
 
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,cache", [
+    (96, 96, 3, (1, 1, 1), 1, 2), (3, 96, 3, (1, 1, 1), 1, 0), (192, 192, (3, 1, 1), (2, 1, 1), (0, 0, 0), 0),
+    (384, 32, 1, (1, 1, 1), 0, 0)])
+def test_leaf_causal_conv3d_forward(vops, cin, cout, k, stride, pad, cache):
+    """`CausalConv3d.forward(x, cache_x)` (reference vae2_1.py:26-35) at leaf granularity on the kernels: planar
+    [B, C, T, H, W] in and out, cached frames in place of the causal zero padding; against torch's fp32 conv on the
+    same bf16-rounded operands."""
+    import torch.nn.functional as F
+    from omni_video_b200.modules.vae2_1 import CausalConv3d, RMS_norm
+    torch.manual_seed(5)
+    torch.backends.cudnn.allow_tf32 = False
+    m = CausalConv3d(cin, cout, k, stride=stride, padding=pad).cuda()
+    with torch.no_grad():
+        m.weight.copy_(m.weight.bfloat16().float())
+    x = torch.randn(2, cin, 5, 24, 40, device="cuda").bfloat16().float()
+    cache_x = torch.randn(2, cin, cache, 24, 40, device="cuda").bfloat16().float() if cache else None
+    pt, ph, pw = m.padding
+    xp = x if cache_x is None else torch.cat([cache_x, x], dim=2)
+    want = F.conv3d(F.pad(xp, [pw, pw, ph, ph, 2 * pt - cache, 0]), m.weight, m.bias, stride=m.stride)
+    got = m(x, cache_x)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    assert (got - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+    if cin == 96:                                            # and the norm leaf on the result
+        n = RMS_norm(cout, images=False).cuda()
+        y = n(got)
+        ref = F.normalize(got.bfloat16().float(), dim=1) * n.scale * n.gamma
+        assert y.shape == got.shape and (y - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("c", [16, 96, 192, 384, 768])
 def test_rmsnorm_silu_cl(vops, c):
     rng = _rng(c)

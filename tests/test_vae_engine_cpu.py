@@ -111,3 +111,53 @@ def test_patch_seam_on_the_reference_own_vae_class(monkeypatch, tmp_path):
     patch.patch_reference_vae(vae)
     out = vae.decode([synth.vae_latent(tuple(meta["grid"]), seed=meta["input_seed"])])[0]
     assert out.shape == gold.shape and V.psnr(out, gold) >= 40.0
+
+
+def _reference_causal_conv3d(m, x, cache_x=None):
+    """The reference's CausalConv3d.forward (vae2_1.py:26-35) written out with torch: all time padding in front,
+    cached frames in place of part of it."""
+    import torch.nn.functional as F
+    pt, ph, pw = m.padding
+    pad = [pw, pw, ph, ph, 2 * pt, 0]
+    if cache_x is not None and pad[4] > 0:
+        x = torch.cat([cache_x, x], dim=2)
+        pad[4] -= cache_x.shape[2]
+    return F.conv3d(F.pad(x, pad), m.weight, m.bias, stride=m.stride)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,cache", [
+    (16, 32, 3, (1, 1, 1), 1, 0), (16, 32, 3, (1, 1, 1), 1, 2), (16, 32, 3, (1, 1, 1), 1, 1),
+    (32, 32, (3, 1, 1), (2, 1, 1), (0, 0, 0), 0), (32, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2), (3, 16, 3, (1, 1, 1), 1, 0),
+    (16, 16, 1, (1, 1, 1), 0, 0)])
+def test_leaf_causal_conv3d_forward_matches_the_reference_semantics(monkeypatch, cin, cout, k, stride, pad, cache):
+    """`CausalConv3d.forward(x, cache_x)` at leaf granularity (host logic with emulated kernels): causal padding,
+    cache frames, strides, channel padding of a 3-channel input, planar fp32 output."""
+    from omni_video_b200.modules import vae2_1
+    cpu_emulation.install_vae(monkeypatch)
+    monkeypatch.setattr(vae2_1, "_leaf_device_check", lambda x, what: None)
+    torch.manual_seed(3)
+    m = vae2_1.CausalConv3d(cin, cout, k, stride=stride, padding=pad)
+    with torch.no_grad():
+        m.weight.copy_(m.weight.bfloat16().float())
+    x = torch.randn(2, cin, 5, 6, 7).bfloat16().float()
+    cache_x = torch.randn(2, cin, cache, 6, 7).bfloat16().float() if cache else None
+    want = _reference_causal_conv3d(m, x, cache_x)
+    got = m(x, cache_x)
+    assert got.shape == want.shape and got.dtype == x.dtype
+    assert (got - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
+
+
+def test_leaf_rms_norm_forward_matches_the_reference_semantics(monkeypatch):
+    import torch.nn.functional as F
+    from omni_video_b200.modules import vae2_1
+    cpu_emulation.install_vae(monkeypatch)
+    monkeypatch.setattr(vae2_1, "_leaf_device_check", lambda x, what: None)
+    torch.manual_seed(4)
+    for images, shape in ((False, (2, 32, 3, 4, 5)), (True, (6, 32, 4, 5))):
+        m = vae2_1.RMS_norm(32, images=images)
+        with torch.no_grad():
+            m.gamma.add_(0.1 * torch.randn_like(m.gamma))
+        x = torch.randn(shape).bfloat16().float()
+        want = F.normalize(x, dim=1) * m.scale * m.gamma                   # reference :52-53 (bias=False)
+        got = m(x)
+        assert got.shape == x.shape and (got - want).abs().max().item() <= 2e-2          # bf16 output rounding
