@@ -3,8 +3,9 @@
 `Wan2_1_VAE(z_dim, vae_pth, dtype, device)` with `.encode(videos)` / `.decode(zs)` and the
 attributes the pipeline touches (`.model`, `.mean`, `.std`, `.scale`, `.model.z_dim`;
 x2x_gen_unified.py:328,506-510) keeps the reference's surface; the module tree below carries the
-reference's parameter names so `Wan2.1_VAE.pth` loads unchanged.  None of the leaf `forward`s runs
-on the hot path: `VAEEngine` walks the parameters and drives libovb200:
+reference's parameter names so `Wan2.1_VAE.pth` loads unchanged.  No leaf `forward` runs on the hot path
+(`CausalConv3d` and `RMS_norm` have one, on the same kernels, for callers that walk the tree themselves):
+`VAEEngine` walks the parameters and drives libovb200:
 
     reference op (vae2_1.py)                               kernel
     -----------------------------------------------------  ---------------------------------------
