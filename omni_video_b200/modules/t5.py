@@ -20,7 +20,7 @@ working without PyTorch arithmetic on the device.  Parameter names are the refer
                                                                  ovb_gemm_bf16 GATE_RESID_F32 on a zero residual
     fc2 + residual :170                                          ovb_gemm_bf16 RESID_BF16
 
-A block is 12 launches whatever the head count (round 1 looped over the heads: 4 launches x 64 heads x 24 blocks).
+A block is 10 launches whatever the head count (round 1 looped over the heads: 4 launches x 64 heads x 24 blocks).
 The relative-position bias (t5.py:229-263) depends on (key - query) only: per block it is an fp32 [heads, 2L-1]
 vector table, gathered once per sequence length from the bucket embedding (integer arithmetic on positions, on the
 host, like the reference does) and cached next to the packed weights.
@@ -184,14 +184,12 @@ class T5Encoder(nn.Module):
         q, k, v = (qkv[:, i * da:(i + 1) * da].unflatten(1, (nh, hd)).unflatten(0, (B, L)) for i in range(3))
         for W, bias in zip(layers, rel_bias):
             # ---- self attention (no 1/sqrt(d) scaling in T5)
-            h.copy_(x)
-            ops.rmsnorm_rope_(h, W["n1"], eps)
+            ops.rmsnorm_rope_(x, W["n1"], eps, out=h)
             ops.gemm(h, W["qkv"], None, epilogue=EPI_BF16, out=qkv)
             ops.attention_relbias(q, k, v, bias, k_lens, 1.0, out=att.view(B, L, nh, hd))
             ops.gemm(att, W["o"], None, epilogue=EPI_RESID_BF16, out=x, resid=x)
             # ---- gated-GELU feed forward
-            h.copy_(x)
-            ops.rmsnorm_rope_(h, W["n2"], eps)
+            ops.rmsnorm_rope_(x, W["n2"], eps, out=h)
             g = ops.cast_bf16_to_f32(ops.gemm(h, W["gate"], None, epilogue=EPI_GELU_BF16))
             ops.gemm(h, W["fc1"], None, epilogue=EPI_GATE_RESID_F32, out=u, resid=zero, gate=g)
             ops.gemm(ops.cast_f32_to_bf16(u), W["fc2"], None, epilogue=EPI_RESID_BF16, out=x, resid=x)

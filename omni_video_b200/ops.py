@@ -302,8 +302,10 @@ def _ptr_array(ptrs):
 def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, eps: float, *,
                   cs_table: Optional[torch.Tensor] = None, grid=None, rows_per_sample: int = 0,
                   token_offset: int = 0, dst_ptrs: Optional[Sequence[int]] = None, dst_ld: int = 0,
-                  copy_only: bool = False) -> torch.Tensor:
+                  copy_only: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """In place on x: bf16 [rows, d] (ld arbitrary) or [col_split, rows, d/col_split].
+    out (bf16 [rows, d], 2-D x only): write the result there and leave x alone — the scatter form with one local
+    destination (d <= 5120); returns out.
     With cs_table (fp32 [T, 64, 2]) and grid=(F, H, W) also applies the 3-D RoPE.
     Scatter form: dst_ptrs = col_split raw device pointers (possibly peer-mapped memory of other
     GPUs); column group g of row r is written to dst_ptrs[g] + r * dst_ld instead of in place;
@@ -331,12 +333,16 @@ def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, eps: float, *,
         args.F, args.H, args.W = F, H, W
         args.rows_per_sample = rows_per_sample or rows
         args.token_offset = token_offset
+    if out is not None:
+        assert dst_ptrs is None and x.dim() == 2 and out.dtype == bf16 and out.shape == x.shape and out.stride(1) == 1
+        _need_cuda(out)
+        dst_ptrs, dst_ld = [out.data_ptr()], out.stride(0)
     if dst_ptrs is not None:
         assert len(dst_ptrs) == args.col_split
         keep = _ptr_array(dst_ptrs)
         args.dst_ptrs, args.dst_ld, args.copy_only = keep, dst_ld, int(copy_only)
     _lib.check(lib.ovb_rmsnorm_rope(C.byref(args), _stream()), "ovb_rmsnorm_rope")
-    return x
+    return x if out is None else out
 
 
 def peer_signal_wait(pad_ptrs: Sequence[int], rank: int, state: torch.Tensor):

@@ -353,6 +353,13 @@ def test_scatter_forms_on_one_gpu_match_the_plain_forms(ops):
     for g in range(groups):
         assert torch.equal(dst[g][:rows, :dc], x[g])
 
+    # `out=`: the same form with one local destination (how the umT5 encoder keeps its residual stream untouched)
+    x2 = _randn(rng, 300, 4096).to(bf16).cuda()
+    w2 = (1 + 0.1 * _randn(rng, 4096)).to(bf16).cuda()
+    keep, dst2 = x2.clone(), torch.empty_like(x2)
+    assert ops.rmsnorm_rope_(x2, w2, 1e-6, out=dst2) is dst2
+    assert torch.equal(x2, keep) and torch.equal(dst2, ops.rmsnorm_rope_(keep.clone(), w2, 1e-6))
+
     L, H, per = 600, 2, 300
     q, k, v = (_randn(rng, 1, L, H, 128).to(bf16).cuda() for _ in range(3))
     whole = ops.attention(q, k, v, k_lens=[555])

@@ -40,11 +40,12 @@ def _emulate(monkeypatch):
         out.copy_(res)
         return out
 
-    def rmsnorm_rope_(x, weight, eps, **kw):
+    def rmsnorm_rope_(x, weight, eps, out=None, **kw):
         assert not kw and x.dtype == bf16
         xf = x.float()
-        x.copy_(((xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(bf16).float() * weight.float()).to(bf16))
-        return x
+        dst = x if out is None else out                     # out: the input stays untouched (the residual stream)
+        dst.copy_(((xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(bf16).float() * weight.float()).to(bf16))
+        return dst
 
     def attention_relbias(q, k, v, rel_bias, k_lens=None, softmax_scale=1.0, out=None):
         """ovb_attn_relbias_fwd (include/ovb200.h): fp32 scores + bias[h, (j - i) + L - 1], keys >= k_lens[b]
