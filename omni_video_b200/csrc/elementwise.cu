@@ -133,9 +133,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // One WARP per row, the row held in registers (VPL float4 vectors per lane, lane l owns vectors
 // l, l+32, ...: every warp-wide load is one contiguous 512-byte run).  No shared memory and no
 // __syncthreads: the two reductions are five shuffles each.  The launch is persistent: one grid-stride
-// pass of sm_count x resident CTAs (two per SM up to d = 2048), which is what lifted d = 5120 from 0.55
-// to 0.63 of copy bandwidth.  At d = 1536 the kernel sits at 0.75-0.77 whatever the occupancy (two,
-// three or four CTAs per SM and either vector layout were measured within 3 %: scripts/norm_time.py).
+// pass of sm_count x resident CTAs (two per SM up to d = 2048).  Occupancy (two, three or four CTAs per SM) and the
+// vector layout were measured within 3 % of each other at d = 1536 (scripts/norm_time.py): what the kernel was
+// short of was issue slots, see FAST below.
 // (The one-CTA-per-row form above spends most of its time in the two block barriers: 0.59 / 0.36 of copy
 // bandwidth for LayerNorm / RMSNorm at d = 1536.)
 __device__ __forceinline__ float4 load4_bf16(const __nv_bfloat16* p) {
@@ -144,10 +144,20 @@ __device__ __forceinline__ float4 load4_bf16(const __nv_bfloat16* p) {
                      __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
 }
 
-template <int VPL>
+// FAST: the shapes the DiT step runs (fp32 residual stream in, bf16 out, d == VPL * 128 so no lane is ever out of
+// range) with mode and rounding as template constants.  The general instantiation carries four run-time flags and a
+// bounds check per vector — ~1200 SASS instructions per row and lane at d = 1536, 25 per element, which is what made
+// a streaming kernel issue-bound (ncu: issue slots 54 % busy); the arithmetic and its order are the same.
+template <int VPL, bool FAST = false, int MODE_T = 0, bool ROUND_T = false>
 __global__ void __launch_bounds__(256, VPL <= 16 ? 2 : 1) layernorm_warp_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * 8;
+  const bool x_bf16 = FAST ? false : p.x_is_bf16 != 0;
+  const bool out_f32 = FAST ? false : p.out_is_f32 != 0;
+  const bool modulate = FAST ? MODE_T == OVB_LN_MODULATE : p.mode == OVB_LN_MODULATE;
+  const bool round_ln = FAST ? ROUND_T : p.round_ln_bf16 != 0;
+  const int d = FAST ? VPL * 128 : p.d;
+  const float inv_d = 1.0f / static_cast<float>(d);
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < p.rows; row += warps) {
     float4 v[VPL];
     float s = 0.f;
@@ -155,37 +165,37 @@ __global__ void __launch_bounds__(256, VPL <= 16 ? 2 : 1) layernorm_warp_kernel(
     for (int i = 0; i < VPL; ++i) {
       const int c0 = (i * 32 + lane) * 4;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 < p.d) {
-        if (p.x_is_bf16)
+      if (FAST || c0 < d) {
+        if (x_bf16)
           v[i] = load4_bf16(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx + c0);
         else
           v[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + row * p.ldx + c0);
       }
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
-    const float mean = warp_sum(s) / p.d;
+    const float mean = warp_sum(s) * inv_d;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if ((i * 32 + lane) * 4 < p.d) {
+      if (FAST || (i * 32 + lane) * 4 < d) {
         const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
         q += (a * a + b * b) + (c * c + e * e);
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / p.d + p.eps);
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + p.eps);
     const int sample = row / p.rows_per_sample;
     const long long mod_off = sample * p.mod_sample_stride + (row - sample * p.rows_per_sample) * p.mod_row_stride;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c0 = (i * 32 + lane) * 4;
-      if (c0 >= p.d) continue;
+      if (!FAST && c0 >= d) continue;
       float y[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
-      if (p.round_ln_bf16) {
+      if (round_ln) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j]);
       }
       float4 a, b;
-      if (p.mode == OVB_LN_MODULATE) {
+      if (modulate) {
         a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.a) + mod_off + c0);
         b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.b) + mod_off + c0);
         a.x += 1.0f; a.y += 1.0f; a.z += 1.0f; a.w += 1.0f;
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(256, VPL <= 16 ? 2 : 1) layernorm_warp_kernel(
         b = load4_bf16(reinterpret_cast<const __nv_bfloat16*>(p.b) + c0);
       }
       y[0] = y[0] * a.x + b.x; y[1] = y[1] * a.y + b.y; y[2] = y[2] * a.z + b.z; y[3] = y[3] * a.w + b.w;
-      if (p.out_is_f32)
+      if (out_f32)
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + c0) = make_float4(y[0], y[1], y[2], y[3]);
       else
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + c0) =
@@ -596,12 +606,26 @@ extern "C" int ovb_layernorm(const ovb_ln_args* a, void* stream) {
   p.round_ln_bf16 = a->round_ln_bf16;
   const int vpl = (a->d / 4 + 31) / 32;  // float4 vectors per lane with one warp per row
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define OVB_LN_LAUNCH(V)                                                                           \
-  do {                                                                                             \
-    static int occ[64] = {};                                                                       \
-    layernorm_warp_kernel<V><<<warp_row_grid(a->rows, layernorm_warp_kernel<V>, occ), 256, 0, st>>>(p); \
+#define OVB_LN_LAUNCH(...)                                                                                         \
+  do {                                                                                                             \
+    static int occ[64] = {};                                                                                       \
+    layernorm_warp_kernel<__VA_ARGS__><<<warp_row_grid(a->rows, layernorm_warp_kernel<__VA_ARGS__>, occ), 256, 0, st>>>(p); \
   } while (0)
-  if (vpl <= 2) OVB_LN_LAUNCH(2);
+#define OVB_LN_FAST(V)                                                            \
+  do {                                                                            \
+    if (p.mode == OVB_LN_MODULATE) {                                              \
+      if (p.round_ln_bf16) OVB_LN_LAUNCH(V, true, OVB_LN_MODULATE, true);         \
+      else OVB_LN_LAUNCH(V, true, OVB_LN_MODULATE, false);                        \
+    } else {                                                                      \
+      if (p.round_ln_bf16) OVB_LN_LAUNCH(V, true, OVB_LN_AFFINE, true);           \
+      else OVB_LN_LAUNCH(V, true, OVB_LN_AFFINE, false);                          \
+    }                                                                             \
+  } while (0)
+  // the step's shapes: fp32 in, bf16 out, d = 1536 (OmniVideo2-1.3B) or 5120 (A14B)
+  const bool fast = !p.x_is_bf16 && !p.out_is_f32 && getenv("OVB_LN_GENERAL") == nullptr;
+  if (fast && a->d == 12 * 128) OVB_LN_FAST(12);
+  else if (fast && a->d == 40 * 128) OVB_LN_FAST(40);
+  else if (vpl <= 2) OVB_LN_LAUNCH(2);
   else if (vpl <= 4) OVB_LN_LAUNCH(4);
   else if (vpl <= 8) OVB_LN_LAUNCH(8);
   else if (vpl <= 12) OVB_LN_LAUNCH(12);
@@ -609,6 +633,7 @@ extern "C" int ovb_layernorm(const ovb_ln_args* a, void* stream) {
   else if (vpl <= 24) OVB_LN_LAUNCH(24);
   else if (vpl <= 32) OVB_LN_LAUNCH(32);
   else if (vpl <= 40) OVB_LN_LAUNCH(40);
+#undef OVB_LN_FAST
 #undef OVB_LN_LAUNCH
   else {  // d > 5120: the row no longer fits one warp's registers in fp32
     const int threads = ((a->d / 8 + 31) / 32) * 32;
