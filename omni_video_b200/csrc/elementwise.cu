@@ -538,6 +538,87 @@ linear_f32_kernel(const float* __restrict__ x, long long ldx, const __nv_bfloat1
   }
 }
 
+// Tall-skinny form of the above for the DiT head ([65520, 1536] fp32 x [64, 1536]^T): 128 rows x 64 columns per CTA,
+// 8 x 4 outputs per thread (12 shared-memory words per 32 FMAs instead of 8 per 16), 16-byte global loads with the
+// next K chunk's loads in flight while the current one is multiplied.  Every output is still ONE fp32 FMA chain over
+// ascending k, so the result is bit-identical to linear_f32_kernel's.  Needs K % 32 == 0, ldx % 4 == 0, ldw % 8 == 0.
+constexpr int kTSM = 128, kTSN = 64, kTSK = 32;
+__global__ void __launch_bounds__(256, 2)
+linear_f32_tall_kernel(const float* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ Wt, long long ldw,
+                       const __nv_bfloat16* __restrict__ bias, float* __restrict__ out, long long ldo, int M, int N,
+                       int K, int act_in, int act_out) {
+  __shared__ __align__(16) float sx[kTSK][kTSM + 4];
+  __shared__ __align__(16) float sw[kTSK][kTSN + 4];
+  const int m0 = blockIdx.y * kTSM, n0 = blockIdx.x * kTSN;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  // staging roles: x tile = 128 rows x 8 float4 (4 per thread), W tile = 64 rows x 4 uint4 of 8 bf16 (1 per thread)
+  const int xr = threadIdx.x / 8, xk = (threadIdx.x % 8) * 4;          // rows xr + 32 e, e = 0..3
+  const int wr = threadIdx.x / 4, wk = (threadIdx.x % 4) * 8;
+  float4 xv[4];
+  uint4 wv;
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = m0 + xr + 32 * e;
+      xv[e] = r < M ? *reinterpret_cast<const float4*>(x + r * ldx + k0 + xk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    wv = n0 + wr < N ? *reinterpret_cast<const uint4*>(Wt + (n0 + wr) * ldw + k0 + wk) : make_uint4(0u, 0u, 0u, 0u);
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kTSK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float4 v = xv[e];
+      if (act_in == 1) v = make_float4(act_silu(v.x), act_silu(v.y), act_silu(v.z), act_silu(v.w));
+      const int r = xr + 32 * e;
+      sx[xk][r] = v.x; sx[xk + 1][r] = v.y; sx[xk + 2][r] = v.z; sx[xk + 3][r] = v.w;
+    }
+    {
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&wv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        sw[wk + 2 * q][wr] = __uint_as_float(u[q] << 16);
+        sw[wk + 2 * q + 1][wr] = __uint_as_float(u[q] & 0xffff0000u);
+      }
+    }
+    __syncthreads();
+    if (k0 + kTSK < K) fetch(k0 + kTSK);      // in flight during the multiply
+#pragma unroll
+    for (int kk = 0; kk < kTSK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sx[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sx[kk][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sw[kk][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += __bfloat162float(bias[n]);
+      if (act_out == 1) v = act_silu(v);
+      out[m * ldo + n] = v;
+    }
+  }
+}
+
 // modulation table: out[l, b, k, c] = float(mod[l, k, c]) + e[b, e_has_k ? k*d + c : c]
 // (reference model.py:238 `modulation + e0` per block, :286 for the head), built once per forward.
 __global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ mod,
@@ -781,10 +862,20 @@ extern "C" int ovb_linear_f32(const float* x, int64_t ldx, const void* W, int64_
                               int32_t K, int32_t act_in, int32_t act_out, void* stream) {
   OVB_CHECK_ARG(x && W && out, "ovb_linear_f32: null pointer");
   OVB_CHECK_ARG(M > 0 && N > 0 && K > 0, "ovb_linear_f32: bad shape");
-  dim3 grid((N + kLT - 1) / kLT, (M + kLT - 1) / kLT);
-  linear_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw,
-      reinterpret_cast<const __nv_bfloat16*>(bias), out, ldo, M, N, K, act_in, act_out);
+  const bool tall = M >= 4096 && K % kTSK == 0 && ldx % 4 == 0 && ldw % 8 == 0 &&
+                    reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(W) % 16 == 0 &&
+                    getenv("OVB_LINEAR_F32_GENERAL") == nullptr;
+  if (tall) {
+    dim3 grid((N + kTSN - 1) / kTSN, (M + kTSM - 1) / kTSM);
+    linear_f32_tall_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw,
+        reinterpret_cast<const __nv_bfloat16*>(bias), out, ldo, M, N, K, act_in, act_out);
+  } else {
+    dim3 grid((N + kLT - 1) / kLT, (M + kLT - 1) / kLT);
+    linear_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw,
+        reinterpret_cast<const __nv_bfloat16*>(bias), out, ldo, M, N, K, act_in, act_out);
+  }
   OVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return OVB_OK;

@@ -370,6 +370,24 @@ def test_scatter_forms_on_one_gpu_match_the_plain_forms(ops):
         assert torch.equal(t[:, :H * 128].view(per, H, 128), whole[0, i * per:(i + 1) * per])
 
 
+@pytest.mark.parametrize("M,N,K,act_in,act_out", [(5000, 64, 1536, 0, 0), (4100, 40, 256, 1, 1), (65520, 64, 1536, 0, 0)])
+def test_linear_f32_tall_form_matches_the_general_kernel_bit_for_bit(ops, monkeypatch, M, N, K, act_in, act_out):
+    """The DiT head's shape (many rows, <= 64 outputs) takes the register-blocked kernel; each output is the same
+    fp32 FMA chain over ascending k as in the general kernel, so the bits agree — and both agree with fp64."""
+    rng = _rng(41 + N)
+    x = _randn(rng, M, K).cuda()
+    w = _randn(rng, N, K, scale=K ** -0.5).to(bf16).cuda()
+    b = _randn(rng, N).to(bf16).cuda()
+    tall = ops.linear_f32(x, w, b, act_in=act_in, act_out=act_out)
+    monkeypatch.setenv("OVB_LINEAR_F32_GENERAL", "1")
+    general = ops.linear_f32(x, w, b, act_in=act_in, act_out=act_out)
+    monkeypatch.delenv("OVB_LINEAR_F32_GENERAL")
+    assert tall.shape == (M, N) and torch.equal(tall, general)
+    if not act_in and not act_out:
+        want = x[:512].double() @ w.double().T + b.double()
+        assert (tall[:512].double() - want).abs().max().item() <= 3e-6 * want.abs().max().item()
+
+
 def test_patchify_unpatchify(ops):
     rng = _rng(9)
     u = _randn(rng, 16, 3, 8, 12)
