@@ -619,6 +619,45 @@ linear_f32_tall_kernel(const float* __restrict__ x, long long ldx, const __nv_bf
   }
 }
 
+// Few-row form (the time-embedding MLPs: one row per sample, model.py:390-392): a 64-row tile would idle 62 of its
+// rows and leave the launch on N/64 CTAs.  One warp per output column, lanes split K (16-byte loads of the bf16
+// weight row, the fp32 input rows come from L1), five shuffles per row: the weights are read once at HBM speed.
+constexpr int kFewRows = 8;
+__global__ void __launch_bounds__(256)
+linear_f32_fewrows_kernel(const float* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ Wt,
+                          long long ldw, const __nv_bfloat16* __restrict__ bias, float* __restrict__ out, long long ldo,
+                          int M, int N, int K, int act_in, int act_out) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[kFewRows];
+#pragma unroll
+  for (int m = 0; m < kFewRows; ++m) acc[m] = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    float w[8];
+    load8_bf16(Wt + n * ldw + k, w);
+#pragma unroll
+    for (int m = 0; m < kFewRows; ++m) {
+      if (m < M) {
+        float v[8];
+        load8_f32(x + m * ldx + k, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[m] = fmaf(act_in == 1 ? act_silu(v[j]) : v[j], w[j], acc[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < kFewRows; ++m) {
+    const float t = warp_sum(acc[m]);
+    if (lane == 0 && m < M) {
+      float v = t;
+      if (bias != nullptr) v += __bfloat162float(bias[n]);
+      if (act_out == 1) v = act_silu(v);
+      out[m * ldo + n] = v;
+    }
+  }
+}
+
 // modulation table: out[l, b, k, c] = float(mod[l, k, c]) + e[b, e_has_k ? k*d + c : c]
 // (reference model.py:238 `modulation + e0` per block, :286 for the head), built once per forward.
 __global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ mod,
@@ -865,7 +904,14 @@ extern "C" int ovb_linear_f32(const float* x, int64_t ldx, const void* W, int64_
   const bool tall = M >= 4096 && K % kTSK == 0 && ldx % 4 == 0 && ldw % 8 == 0 &&
                     reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(W) % 16 == 0 &&
                     getenv("OVB_LINEAR_F32_GENERAL") == nullptr;
-  if (tall) {
+  const bool few = M <= kFewRows && K % 8 == 0 && ldx % 4 == 0 && ldw % 8 == 0 &&
+                   reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(W) % 16 == 0 &&
+                   getenv("OVB_LINEAR_F32_GENERAL") == nullptr;
+  if (few) {
+    linear_f32_fewrows_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw,
+        reinterpret_cast<const __nv_bfloat16*>(bias), out, ldo, M, N, K, act_in, act_out);
+  } else if (tall) {
     dim3 grid((N + kTSN - 1) / kTSN, (M + kTSM - 1) / kTSM);
     linear_f32_tall_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw,

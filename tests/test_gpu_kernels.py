@@ -388,6 +388,27 @@ def test_linear_f32_tall_form_matches_the_general_kernel_bit_for_bit(ops, monkey
         assert (tall[:512].double() - want).abs().max().item() <= 3e-6 * want.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K,act_in,act_out", [(2, 9216, 1536, 1, 0), (1, 1536, 256, 0, 1), (8, 100, 264, 0, 0)])
+def test_linear_f32_few_rows_form(ops, monkeypatch, M, N, K, act_in, act_out):
+    """The time-embedding MLPs (one row per sample, reference model.py:390-392) take the warp-per-output-column
+    kernel; its lane-parallel fp32 sums agree with the general kernel's chains and with fp64 to fp32 accuracy."""
+    rng = _rng(51 + M)
+    x = _randn(rng, M, K).cuda()
+    w = _randn(rng, N, K, scale=K ** -0.5).to(bf16).cuda()
+    b = _randn(rng, N).to(bf16).cuda()
+    few = ops.linear_f32(x, w, b, act_in=act_in, act_out=act_out)
+    monkeypatch.setenv("OVB_LINEAR_F32_GENERAL", "1")
+    general = ops.linear_f32(x, w, b, act_in=act_in, act_out=act_out)
+    monkeypatch.delenv("OVB_LINEAR_F32_GENERAL")
+    xin = F.silu(x.double()) if act_in else x.double()
+    want = xin @ w.double().T + b.double()
+    want = F.silu(want) if act_out else want
+    scale = want.abs().max().item()
+    assert few.shape == (M, N)
+    assert (few.double() - want).abs().max().item() <= 3e-6 * scale
+    assert (few - general).abs().max().item() <= 3e-6 * scale
+
+
 def test_patchify_unpatchify(ops):
     rng = _rng(9)
     u = _randn(rng, 16, 3, 8, 12)
