@@ -18,7 +18,8 @@ What changes here is only HOW the same arithmetic is scheduled:
   (`_prepare_model_for_timestep`, offload_model / init_on_cpu); 2 x 28 GB of bf16 weights fit a 180 GB B200
   next to the activations, so both stay resident and the switch is a Python reference.
 * **Fused update** — guidance, x0 prediction, UniC corrector and UniP predictor are single-launch linear
-  combinations (`FlowUniPCMultistepScheduler.step_cfg`).
+  combinations (`FlowUniPCMultistepScheduler.step_cfg`); likewise the DPM-Solver++ update of
+  `sample_solver='dpm++'` (`FlowDPMSolverMultistepScheduler.step_cfg`).
 
 The conditioning front-end consumes `random.random()` exactly as the reference does whether the two branches
 are batched or not (2 draws per sample per call: 4 per step either way).
@@ -29,6 +30,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
+from .utils.fm_solvers import FlowDPMSolverMultistepScheduler, get_sampling_sigmas, retrieve_timesteps
 from .utils.fm_solvers_unipc import FlowUniPCMultistepScheduler
 
 __all__ = ["DenoiseLoop", "merge_cfg_args"]
@@ -117,14 +119,20 @@ class DenoiseLoop:
         """noise: [C, F, H, W] on the device (x2x_gen_unified.py:382-391) -> [latents], ready for
         `Wan2_1_VAE.decode`.  arg_c / arg_null: the keyword sets of :452-472 (for a bare WanModel:
         `context` and `seq_len`)."""
-        if sample_solver != "unipc":
-            raise NotImplementedError("only the flow-matching UniPC solver (the launchers' default) is built; "
-                                      "reference x2x_gen_unified.py:417-427 also offers dpm++")
-        sched = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1,
-                                            use_dynamic_shifting=False)
-        sched.set_timesteps(sampling_steps, device=noise.device, shift=shift)
+        if sample_solver == "unipc":                                   # x2x_gen_unified.py:409-416
+            sched = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1,
+                                                use_dynamic_shifting=False)
+            sched.set_timesteps(sampling_steps, device=noise.device, shift=shift)
+            timesteps = sched.timesteps
+        elif sample_solver == "dpm++":                                 # :417-427
+            sched = FlowDPMSolverMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1,
+                                                    use_dynamic_shifting=False)
+            timesteps, _ = retrieve_timesteps(sched, device=noise.device,
+                                              sigmas=get_sampling_sigmas(sampling_steps, shift))
+        else:
+            raise NotImplementedError("Unsupported solver.")
         latent = noise
-        for i, t in enumerate(sched.timesteps):
+        for i, t in enumerate(timesteps):
             timestep = t.unsqueeze(0)
             cond, uncond = self.predict(latent, timestep, arg_c, arg_null)
             latent = sched.step_cfg(cond, uncond, guide_scale, t, latent.unsqueeze(0))[0].squeeze(0)

@@ -21,9 +21,10 @@ from oracle.unipc import synthetic_flow  # noqa: E402
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def load_reference_scheduler():
+def load_reference_scheduler(filename="fm_solvers_unipc.py", cls_name="FlowUniPCMultistepScheduler", module=False):
     """diffusers is absent: provide the three names the file imports (ConfigMixin with a working
-    `register_to_config`, SchedulerMixin/SchedulerOutput, deprecate)."""
+    `register_to_config`, SchedulerMixin/SchedulerOutput, deprecate).  Also serves oracle/gen_golden_dpm.py
+    (fm_solvers.py; `module=True` returns the module next to the class)."""
     class ConfigMixin:
         def register_to_config(self, **kw):
             for k, v in kw.items():
@@ -52,7 +53,9 @@ def load_reference_scheduler():
         "diffusers.schedulers": types.ModuleType("diffusers.schedulers"),
         "diffusers.schedulers.scheduling_utils": types.ModuleType("diffusers.schedulers.scheduling_utils"),
         "diffusers.utils": types.ModuleType("diffusers.utils"),
+        "diffusers.utils.torch_utils": types.ModuleType("diffusers.utils.torch_utils"),
     }
+    mods["diffusers.utils.torch_utils"].randn_tensor = None        # only the SDE variants draw noise
     mods["diffusers.configuration_utils"].ConfigMixin = ConfigMixin
     mods["diffusers.configuration_utils"].register_to_config = register_to_config
     su = mods["diffusers.schedulers.scheduling_utils"]
@@ -63,7 +66,7 @@ def load_reference_scheduler():
     sys.modules.update(mods)
     try:
         spec = importlib.util.spec_from_file_location(
-            "ref_fm_solvers_unipc", os.path.join(REF_ROOT, "omnivideo", "utils", "fm_solvers_unipc.py"))
+            "ref_" + filename[:-3], os.path.join(REF_ROOT, "omnivideo", "utils", filename))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
     finally:
@@ -73,10 +76,10 @@ def load_reference_scheduler():
             else:
                 sys.modules[k] = v
     # the reference applies @register_to_config?  it calls self.config.* — make sure config exists
-    cls = mod.FlowUniPCMultistepScheduler
+    cls = getattr(mod, cls_name)
     if not hasattr(cls.__init__, "__wrapped__") and "config" not in cls.__init__.__code__.co_names:
         cls.__init__ = register_to_config(cls.__init__)
-    return cls
+    return (cls, mod) if module else cls
 
 
 CASES = [

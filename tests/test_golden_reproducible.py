@@ -17,7 +17,8 @@ pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tr
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("module,prefix", [("oracle.gen_golden_unified", "unified_"), ("oracle.gen_golden_t5", "t5_"),
-                                           ("oracle.gen_golden_video", "video_"), ("oracle.gen_golden_unipc", "unipc_")])
+                                           ("oracle.gen_golden_video", "video_"), ("oracle.gen_golden_unipc", "unipc_"),
+                                           ("oracle.gen_golden_dpm", "dpm_")])
 def test_generator_reproduces_committed_fixtures(tmp_path, monkeypatch, module, prefix):
     import sys
     gen = importlib.import_module(module)

@@ -60,3 +60,23 @@ def test_lincomb_kernel(  ):
     outb = ops.lincomb([(2.0, xb), (1.0, x[0])], out_dtype=torch.bfloat16, round_bf16=[0])
     refb = ((2.0 * xb.float()).bfloat16().float() + x[0]).bfloat16()
     assert (outb.float() - refb.float()).abs().max().item() <= 2 ** -7 * refb.float().abs().max().item()
+
+
+@pytest.mark.parametrize("name", golden_names("dpm"))
+def test_dpm_scheduler_trajectory_vs_reference_golden(name):
+    """`sample_solver='dpm++'` (reference utils/fm_solvers.py, x2x_gen_unified.py:417-427): the DPM-Solver++ update
+    as ovb_lincomb launches against trajectories of the reference scheduler — second order midpoint (the default),
+    third order on a bf16 latent, heun."""
+    from omni_video_b200.utils.fm_solvers import (FlowDPMSolverMultistepScheduler, get_sampling_sigmas,
+                                                  retrieve_timesteps)
+    meta, traj = load(name)
+    kw = {k: meta[k] for k in ("solver_order", "solver_type") if k in meta}
+    sch = FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False, **kw)
+    timesteps, _ = retrieve_timesteps(sch, device="cuda", sigmas=get_sampling_sigmas(meta["steps"], meta["shift"]))
+    assert timesteps.is_cuda and [int(t) for t in timesteps] == meta["timesteps"]
+    x = synthetic_flow(-1, tuple(meta["shape"])).to(getattr(torch, meta["dtype"])).cuda()
+    for i, (t, want) in enumerate(zip(timesteps, traj)):
+        x = sch.step(synthetic_flow(i, tuple(meta["shape"])).cuda(), t, x, return_dict=False)[0]
+        assert x.dtype == getattr(torch, meta["out_dtype"]) and x.shape == tuple(meta["shape"])
+        err = (x.float().cpu() - want).abs().max().item()
+        assert err <= 2e-5 * max(1.0, want.abs().max().item()), f"step {i}: {err}"

@@ -79,8 +79,8 @@ def test_single_expert_and_unsupported_solver(loop_mod):
     e = _Expert(1.0, 0.0)
     loop = loop_mod.DenoiseLoop(e)
     assert loop.low_noise_model is e
-    with pytest.raises(NotImplementedError):
-        loop.sample(torch.zeros(16, 1, 2, 2), {}, {}, sample_solver="dpm++")
+    with pytest.raises(NotImplementedError):           # x2x_gen_unified.py:428: anything but unipc / dpm++
+        loop.sample(torch.zeros(16, 1, 2, 2), {}, {}, sample_solver="euler")
 
 
 def test_merge_cfg_args():
